@@ -1,0 +1,227 @@
+/*
+ * tinsel_b200.h -- C ABI of the B200-native wavefront path tracer.
+ *
+ * This is the drop-in boundary for tinsel's one data-parallel hot path
+ * (ray-gen -> two-level BVH traversal -> Disney BSDF -> MIS next-event
+ * estimation -> filtered framebuffer accumulation).  Plain pointers and sizes
+ * only: no C++ types, no torch types.  The reference-side C++ adapter that
+ * turns these entry points back into tinsel's
+ *     Renderer* CreateGpuWavefrontRenderer(const Scene* s);     (src/render.h:78)
+ *     virtual void Renderer::Init(int width, int height);       (src/render.h:70)
+ *     virtual void Renderer::Render(const Camera&, const Options&, Color*);  (src/render.h:71)
+ * lives in tinsel_b200/plugin/tinsel_plugin.cpp and is shown in INTEGRATION.md.
+ *
+ * Every POD struct below mirrors a reference struct field-for-field in meaning
+ * (not in byte layout: pointers-to-host-Mesh become mesh indices, the unused
+ * bump-map fields are dropped).  File:line citations are under /root/reference.
+ */
+#ifndef TINSEL_B200_H
+#define TINSEL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- POD mirrors of the reference's input types ------------------------------------------ */
+
+/* Transform (src/maths.h:575-589): rigid transform with uniform scale. */
+typedef struct tb200_transform {
+    float p[3];      /* translation                     */
+    float r[4];      /* rotation quaternion x,y,z,w     */
+    float s;         /* uniform scale                   */
+} tb200_transform;
+
+/* Material (src/scene.h:45-102) without the unused bump-map fields. */
+typedef struct tb200_material {
+    float emission[3];
+    float color[3];
+    float absorption[3];
+    float eta;
+    float metallic;
+    float subsurface;
+    float specular;
+    float roughness;
+    float specularTint;
+    float anisotropic;     /* parsed, unused by the reference BSDF (src/disney.h) */
+    float sheen;           /* parsed, unused */
+    float sheenTint;       /* parsed, unused */
+    float clearcoat;
+    float clearcoatGloss;
+    float transmission;
+} tb200_material;
+
+/* GeometryType (src/scene.h:104-109) */
+enum { TB200_SPHERE = 0, TB200_PLANE = 1, TB200_MESH = 2 };
+
+/* Primitive (src/scene.h:142-159).  `mesh` indexes tb200_scene::meshes (the reference
+ * identifies shared meshes by MeshGeometry::id, src/util.h:20). */
+typedef struct tb200_primitive {
+    tb200_transform start;       /* startTransform */
+    tb200_transform end;         /* endTransform   */
+    int32_t type;                /* TB200_SPHERE / TB200_PLANE / TB200_MESH */
+    float radius;                /* SphereGeometry::radius  */
+    float plane[4];              /* PlaneGeometry::plane    */
+    int32_t mesh;                /* index into meshes, -1 if not a mesh */
+    tb200_material material;
+    int32_t lightSamples;        /* >0: explicitly sampled area light */
+} tb200_primitive;
+
+/* BVHNode (src/bvh.h:9-19), identical 32-byte layout: the reference's bitfield
+ * `rightIndex:31, leaf:1` is the low 31 bits / top bit of right_leaf. */
+typedef struct tb200_bvh_node {
+    float lower[3];
+    float upper[3];
+    uint32_t left;               /* leaf: item index; interior: left child node index */
+    uint32_t right_leaf;         /* bits 0..30 right child node index, bit 31 leaf flag */
+} tb200_bvh_node;
+
+/* MeshGeometry (src/scene.h:121-139).  All pointers are borrowed host memory. */
+typedef struct tb200_mesh {
+    const float* positions;      /* numVertices * 3 */
+    const float* normals;        /* numVertices * 3 */
+    const int32_t* indices;      /* numIndices      */
+    const tb200_bvh_node* nodes; /* numNodes        */
+    const float* cdf;            /* numIndices / 3, area CDF (src/mesh.cpp RebuildCDF) */
+    int32_t numVertices;
+    int32_t numIndices;
+    int32_t numNodes;
+    float area;
+} tb200_mesh;
+
+/* Sky + Probe (src/scene.h:161-181, src/probe.h:9-86). */
+typedef struct tb200_sky {
+    float horizon[3];
+    float zenith[3];
+    int32_t probeValid;
+    int32_t probeWidth;
+    int32_t probeHeight;
+    const float* probeData;      /* width*height*4 (Color rgba) */
+    const float* pdfValuesX;     /* width*height */
+    const float* cdfValuesX;     /* width*height */
+    const float* pdfValuesY;     /* height */
+    const float* cdfValuesY;     /* height */
+} tb200_sky;
+
+/* Scene (src/scene.h:183-217): primitives + scene-level BVH over them + sky. */
+typedef struct tb200_scene {
+    const tb200_primitive* primitives;
+    int32_t numPrimitives;
+    const tb200_mesh* meshes;
+    int32_t numMeshes;
+    const tb200_bvh_node* bvhNodes;  /* Scene::bvh.nodes */
+    int32_t numBvhNodes;
+    tb200_sky sky;
+} tb200_scene;
+
+/* Camera (src/scene.h:11-31) */
+typedef struct tb200_camera {
+    float position[3];
+    float rotation[4];
+    float fov;
+    float shutterStart;
+    float shutterEnd;
+} tb200_camera;
+
+/* Options + Filter (src/render.h:13-63); same field order as the reference. */
+enum { TB200_FILTER_BOX = 0, TB200_FILTER_GAUSSIAN = 1 };
+enum { TB200_MODE_NORMALS = 0, TB200_MODE_COMPLEXITY = 1, TB200_MODE_PATHTRACE = 2 };
+typedef struct tb200_options {
+    int32_t mode;
+    int32_t width;
+    int32_t height;
+    int32_t filterType;
+    float filterWidth;
+    float filterFalloff;
+    float filterOffset;   /* used as handed in, never recomputed (loader quirk, src/loader.cpp:75) */
+    float exposure;
+    float limit;
+    float clamp;
+    int32_t maxDepth;
+    int32_t maxSamples;
+} tb200_options;
+
+/* Per-renderer counters since tb200_init (all monotonically increasing). */
+typedef struct tb200_stats {
+    uint64_t frames;          /* Render() calls (1 spp each) since Init      */
+    uint64_t samples;         /* camera paths traced                          */
+    uint64_t kernelLaunches;  /* CUDA kernels launched by this renderer       */
+    uint64_t d2hBytes;        /* bytes copied device->host                    */
+    uint64_t h2dBytes;        /* bytes copied host->device (scene upload etc) */
+    double   gpuMs;           /* CUDA-event time of the last render call      */
+} tb200_stats;
+
+typedef struct tb200_renderer tb200_renderer;
+
+/* ---- entry points ------------------------------------------------------------------------- */
+
+/* Replaces CreateGpuWavefrontRenderer(const Scene*) (src/render.h:78; the reference's own
+ * definition, src/wavefront.cu:1384, is in no build).  Uploads and re-lays-out the scene for
+ * the GPU.  `device` is the CUDA ordinal.  Returns NULL on failure (see tb200_last_error). */
+tb200_renderer* tb200_create(const tb200_scene* scene, int device);
+
+/* Replaces Renderer::Init (src/render.h:70; semantics of src/render.cu:1070-1075):
+ * (re)allocates and zeroes the device accumulator, resets the frame counter. Returns 0 on success. */
+int tb200_init(tb200_renderer* r, int width, int height);
+
+/* Replaces Renderer::Render (src/render.h:71; semantics of src/render.cpp:447-524):
+ * ePathTrace adds exactly one sample per pixel and leaves output[0..w*h) = running sums
+ * (sum w*r, sum w*g, sum w*b, sum w) since Init; eNormals overwrites with normals; eComplexity
+ * is a no-op.  `output` is HOST memory, width*height*4 floats.  Synchronous. Returns 0 on success. */
+int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, float* output);
+
+/* Batch form of the same path: adds `spp` samples per pixel (frames k..k+spp-1 of the same
+ * per-sample seed sequence as `spp` tb200_render calls) and leaves the sums on the device.
+ * If firstRow/numRows restrict the pixel rows whose samples are traced (image-plane sharding
+ * across GPUs); splats still land wherever the filter footprint reaches.  Returns 0 on success. */
+int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options,
+                        int spp, int firstRow, int numRows);
+
+/* Device pointer of the accumulator (width*height*4 floats) so that callers can reduce it
+ * across GPUs (NCCL) without a host round trip.  Valid until the next tb200_init/destroy. */
+float* tb200_device_accumulator(tb200_renderer* r);
+
+/* Copies the accumulator to host memory (width*height*4 floats).  Returns 0 on success. */
+int tb200_read_accumulator(tb200_renderer* r, float* output);
+
+/* Per-sample radiance probe used by the parity tests: traces frame `frame` only and writes,
+ * for pixel p (row-major), radiance[3p..3p+2] = PathTrace() result and raster[2p..2p+1] =
+ * jittered raster position, WITHOUT touching the accumulator.  Host pointers.  0 on success. */
+int tb200_trace_frame(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options,
+                      int frame, float* radiance, float* raster);
+
+/* Sets the frame counter (frame k seeds sample k of every pixel). */
+void tb200_set_frame(tb200_renderer* r, int frame);
+
+void tb200_get_stats(tb200_renderer* r, tb200_stats* out);
+
+/* Deletes the renderer and all its device memory (reference: `delete g_renderer`, src/main.cpp:323). */
+void tb200_destroy(tb200_renderer* r);
+
+/* Sticky, thread-local description of the last failure ("" if none). */
+const char* tb200_last_error(void);
+
+/* The per-(pixel,frame) seed handed to Random(seed) (src/maths.h:1040-1044).  The reference
+ * CPU renderer has one sequential stream (src/render.cpp:399); a parallel renderer needs a
+ * per-sample rule, and this is it -- shared with the oracle so streams match draw for draw. */
+uint32_t tb200_sample_seed(uint32_t pixelIndex, uint32_t frame);
+
+/* ---- scene snapshots (".tsnap") ----------------------------------------------------------- */
+/* A flat little-endian dump of everything the renderer consumes (tb200_scene + camera +
+ * options as the reference loader produced them).  Written in this container by
+ * oracle/ref_driver (which links the reference's own loader/BVH builder); read anywhere. */
+typedef struct tb200_snapshot tb200_snapshot;
+
+tb200_snapshot* tb200_snapshot_load(const char* path);
+const tb200_scene* tb200_snapshot_scene(const tb200_snapshot* s);
+const tb200_camera* tb200_snapshot_camera(const tb200_snapshot* s);
+const tb200_options* tb200_snapshot_options(const tb200_snapshot* s);
+int tb200_snapshot_save(const char* path, const tb200_scene* scene, const tb200_camera* camera,
+                        const tb200_options* options);
+void tb200_snapshot_free(tb200_snapshot* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINSEL_B200_H */

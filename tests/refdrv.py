@@ -1,0 +1,160 @@
+"""Test-side ctypes wrapper around oracle/_ref/libtinsel_ref*.so (the reference's own code,
+compiled by oracle/Makefile in the build container) and oracle/libtinsel_oracle.so (the CPU
+restatement).  TEST INFRASTRUCTURE: only tests/, bench.py's cpu_baseline/reference arm and
+__graft_entry__.smoke() may import this."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from tinsel_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REFERENCE_ROOT = "/root/reference"
+
+_f32p = C.POINTER(C.c_float)
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def ref_lib_path(flavour):
+    name = "libtinsel_ref.so" if flavour == "literal" else "libtinsel_ref_detmath.so"
+    return os.path.join(REF_DIR, name)
+
+
+def have_ref(flavour="detmath"):
+    return os.path.exists(ref_lib_path(flavour))
+
+
+def have_reference_tree():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src"))
+
+
+_libs = {}
+
+
+def load_ref(flavour="detmath"):
+    if flavour in _libs:
+        return _libs[flavour]
+    lib = C.CDLL(ref_lib_path(flavour))
+    lib.ref_load_tin.restype = C.c_void_p
+    lib.ref_load_tin.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    lib.ref_from_snapshot.restype = C.c_void_p
+    lib.ref_from_snapshot.argtypes = [C.c_char_p]
+    lib.ref_scene.restype = C.POINTER(abi.Scene)
+    lib.ref_scene.argtypes = [C.c_void_p]
+    lib.ref_camera.restype = C.POINTER(abi.Camera)
+    lib.ref_camera.argtypes = [C.c_void_p]
+    lib.ref_options.restype = C.POINTER(abi.Options)
+    lib.ref_options.argtypes = [C.c_void_p]
+    lib.ref_set_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.ref_set_mode.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_set_max_depth.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_save_snapshot.restype = C.c_int
+    lib.ref_save_snapshot.argtypes = [C.c_void_p, C.c_char_p]
+    lib.ref_render_literal.argtypes = [C.c_void_p, C.c_int, _f32p]
+    lib.ref_render_seeded.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int]
+    lib.ref_trace_frame.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int]
+    lib.ref_destroy.argtypes = [C.c_void_p]
+    lib.ref_random_u32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint32)]
+    lib.ref_random_f32.argtypes = [C.c_int, C.c_int, _f32p]
+    lib.ref_material_ior.restype = C.c_float
+    lib.ref_material_ior.argtypes = [C.POINTER(abi.Material)]
+    lib.ref_bsdf_eval.argtypes = [C.POINTER(abi.Material), C.c_float, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p]
+    lib.ref_bsdf_sample.argtypes = [C.POINTER(abi.Material), C.c_float, C.c_float, _f32p, _f32p, C.c_int, _f32p, _f32p,
+                                    C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+    lib.ref_generate_ray.argtypes = [C.POINTER(abi.Camera), C.c_int, C.c_int, C.c_float, C.c_float, _f32p, _f32p]
+    lib.ref_filter_eval.restype = C.c_float
+    lib.ref_filter_eval.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+    lib.ref_trace.restype = C.c_int
+    lib.ref_trace.argtypes = [C.c_void_p, _f32p, _f32p, C.c_float, _f32p, _f32p]
+    lib.ref_probe_sample.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p]
+    lib.ref_sky_eval.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
+    lib.ref_primitive_sample.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, _f32p, _f32p, _f32p]
+    _libs[flavour] = lib
+    return lib
+
+
+class RefScene:
+    """A reference `Scene` + `Camera` + `Options`, from a .tin (build container) or a .tsnap."""
+
+    def __init__(self, lib, handle):
+        if not handle:
+            raise RuntimeError("reference scene failed to load")
+        self.lib = lib
+        self.h = C.c_void_p(handle)
+
+    @classmethod
+    def from_tin(cls, path, width=0, height=0, flavour="detmath"):
+        lib = load_ref(flavour)
+        return cls(lib, lib.ref_load_tin(path.encode(), width, height))
+
+    @classmethod
+    def from_snapshot(cls, path, flavour="detmath"):
+        lib = load_ref(flavour)
+        return cls(lib, lib.ref_from_snapshot(path.encode()))
+
+    @property
+    def scene(self):
+        return self.lib.ref_scene(self.h)
+
+    @property
+    def camera(self):
+        return self.lib.ref_camera(self.h).contents
+
+    @property
+    def options(self):
+        return self.lib.ref_options(self.h).contents
+
+    def set_size(self, w, h):
+        self.lib.ref_set_size(self.h, w, h)
+
+    def set_mode(self, mode):
+        self.lib.ref_set_mode(self.h, mode)
+
+    def set_max_depth(self, d):
+        self.lib.ref_set_max_depth(self.h, d)
+
+    def save_snapshot(self, path):
+        if self.lib.ref_save_snapshot(self.h, path.encode()) != 0:
+            raise RuntimeError("snapshot save failed: " + path)
+
+    def _shape(self):
+        o = self.options
+        return o.height, o.width
+
+    def render_literal(self, spp):
+        h, w = self._shape()
+        out = np.zeros((h, w, 4), np.float32)
+        self.lib.ref_render_literal(self.h, spp, _fp(out))
+        return out
+
+    def render_seeded(self, frame0, nframes, nthreads=1, out=None):
+        h, w = self._shape()
+        if out is None:
+            out = np.zeros((h, w, 4), np.float32)
+        self.lib.ref_render_seeded(self.h, frame0, nframes, _fp(out), nthreads)
+        return out
+
+    def trace_frame(self, frame, nthreads=1):
+        h, w = self._shape()
+        rad = np.zeros((h, w, 3), np.float32)
+        ras = np.zeros((h, w, 2), np.float32)
+        self.lib.ref_trace_frame(self.h, frame, _fp(rad), _fp(ras), nthreads)
+        return rad, ras
+
+    def trace(self, o, d, time=0.0):
+        o = np.asarray(o, np.float32)
+        d = np.asarray(d, np.float32)
+        t = C.c_float()
+        n = np.zeros(3, np.float32)
+        prim = self.lib.ref_trace(self.h, _fp(o), _fp(d), time, C.byref(t), _fp(n))
+        return prim, t.value, n
+
+    def close(self):
+        if self.h:
+            self.lib.ref_destroy(self.h)
+            self.h = None
