@@ -215,7 +215,7 @@ TBM_HD float tbm_atan2f(float y, float x)
 TBM_HD float tbm_acosf(float xf)
 {
     const double x = (double)xf;
-    if (!(fabs(x) <= 1.0)) return (float)(x - x) / 0.0f; /* nan, like libm for |x|>1 */
+    if (!(fabs(x) <= 1.0)) return (float)tbm_bits_to_double(0x7ff8000000000000ull); /* nan, like libm for |x|>1 */
     /* acos x = atan2(sqrt((1-x)(1+x)), x); 1-x and 1+x are exact in double for float x */
     const double s = TBM_SQRT(TBM_MUL(TBM_SUB(1.0, x), TBM_ADD(1.0, x)));
     return (float)tbm_atan2_d(s, x);

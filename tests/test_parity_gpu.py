@@ -1,0 +1,149 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the reference's own arithmetic
+(oracle/_ref detmath flavour = tinsel's src/render.cpp compiled with the deterministic libm the
+kernels use), per sample and bit-exact, plus image-level checks through Renderer.Render."""
+import os
+
+import numpy as np
+import pytest
+
+import tinsel_b200 as tb
+from tinsel_b200 import abi
+import refdrv
+
+pytestmark = pytest.mark.gpu
+
+# scene -> (width, height) used for the per-sample tests (None keeps the .tin's size)
+SCENES = {
+    "cornell": (256, 256),
+    "veach": (192, 128),
+    "glass": (128, 128),
+    "meshlight": (128, 128),
+    "motionblur": (128, 128),
+    "gloss": (128, 128),
+    "emitter": (128, 128),
+    "furnace": (96, 96),
+    "conservation": (128, 64),
+    "ajax": (160, 160),
+    "env": (160, 160),
+}
+
+
+def _available(name):
+    return os.path.exists(tb.scene_path(name))
+
+
+def _setup(name, pipeline, size=None, flavour="detmath"):
+    if not _available(name):
+        pytest.skip("snapshot scenes/%s.tsnap not present" % name)
+    if not refdrv.have_ref(flavour):
+        pytest.skip("oracle/_ref not built")
+    os.environ["TINSEL_B200_PIPELINE"] = pipeline
+    snap = tb.Snapshot(tb.scene_path(name))
+    cam, opt = snap.camera, snap.options
+    w, h = size or SCENES[name]
+    opt.width, opt.height = w, h
+    ref = refdrv.RefScene.from_snapshot(tb.scene_path(name), flavour=flavour)
+    ref.set_size(w, h)
+    r = tb.Renderer(snap.scene)
+    r.Init(w, h)
+    return snap, cam, opt, ref, r
+
+
+def test_sample_seed_matches_host():
+    # host copy (snapshot.cpp) vs the values the device copy is expected to produce are compared
+    # implicitly by every per-sample test; here pin the host function itself
+    assert tb.sample_seed(0, 0) != tb.sample_seed(1, 0)
+    assert tb.sample_seed(5, 7) == tb.sample_seed(5, 7)
+
+
+@pytest.mark.parametrize("pipeline", ["mega", "wavefront"])
+@pytest.mark.parametrize("name", list(SCENES))
+def test_per_sample_radiance_bit_exact(name, pipeline):
+    snap, cam, opt, ref, r = _setup(name, pipeline)
+    for frame in (0, 5):
+        rad, ras = r.trace_frame(cam, opt, frame)
+        rrad, rras = ref.trace_frame(frame, nthreads=8)
+        assert np.array_equal(ras, rras), "raster positions differ"
+        same = (rad.view(np.uint32) == rrad.view(np.uint32)).all(-1) | (np.isnan(rad).any(-1) & np.isnan(rrad).any(-1))
+        bad = int((~same).sum())
+        assert bad == 0, "%s/%s frame %d: %d of %d samples differ (max abs %g)" % (
+            name, pipeline, frame, bad, same.size, float(np.nanmax(np.abs(rad - rrad))))
+    r.close()
+    ref.close()
+    snap.close()
+
+
+@pytest.mark.parametrize("pipeline", ["mega", "wavefront"])
+@pytest.mark.parametrize("name", ["cornell", "veach", "glass", "ajax", "env"])
+def test_render_matches_seeded_oracle(name, pipeline):
+    """Renderer.Render x spp vs oracle B at matched spp and seeds: rel-L2 <= 1e-4 (BASELINE.json)."""
+    snap, cam, opt, ref, r = _setup(name, pipeline)
+    spp = 4
+    out = np.zeros((opt.height, opt.width, 4), np.float32)
+    for _ in range(spp):
+        r.Render(cam, opt, out)
+    oracle = ref.render_seeded(0, spp, nthreads=8)
+    num = np.linalg.norm((out - oracle).astype(np.float64))
+    den = np.linalg.norm(oracle.astype(np.float64))
+    assert num / den <= 1e-4, "rel L2 %g" % (num / den)
+    # the filter-weight channel must agree to fp32 summation noise
+    assert np.allclose(out[..., 3], oracle[..., 3], rtol=1e-5, atol=1e-6)
+    assert r.stats().frames == spp
+    r.close()
+    ref.close()
+    snap.close()
+
+
+@pytest.mark.parametrize("name", ["cornell", "veach", "meshlight", "ajax"])
+def test_normals_mode_bit_exact_vs_literal_reference(name):
+    """eNormals (render.cpp:494-515) has no RNG and no libm: exact match against the literal reference."""
+    snap, cam, opt, ref, r = _setup(name, "wavefront", flavour="literal")
+    opt.mode = abi.MODE_NORMALS
+    ref.set_mode(abi.MODE_NORMALS)
+    out = np.zeros((opt.height, opt.width, 4), np.float32)
+    r.Render(cam, opt, out)
+    expect = ref.render_literal(1)
+    assert np.array_equal(out.view(np.uint32), expect.view(np.uint32)), \
+        "%d pixels differ" % int((out != expect).any(-1).sum())
+    r.close()
+    ref.close()
+    snap.close()
+
+
+def test_batched_render_equals_repeated_render():
+    snap, cam, opt, ref, r = _setup("cornell", "wavefront", size=(128, 128))
+    out = np.zeros((opt.height, opt.width, 4), np.float32)
+    for _ in range(3):
+        r.Render(cam, opt, out)
+    r2 = tb.Renderer(snap.scene)
+    r2.Init(opt.width, opt.height)
+    r2.render_device(cam, opt, 3)
+    out2 = r2.read_accumulator()
+    assert np.allclose(out, out2, rtol=2e-6, atol=1e-6)
+    # row-sharded rendering (image-plane DP) sums to the same image
+    r3 = tb.Renderer(snap.scene)
+    r3.Init(opt.width, opt.height)
+    r3.render_device(cam, opt, 3, 0, 50)
+    r3.set_frame(0)
+    r3.render_device(cam, opt, 3, 50, opt.height - 50)
+    out3 = r3.read_accumulator()
+    assert np.allclose(out, out3, rtol=2e-6, atol=1e-6)
+    for x in (r, r2, r3):
+        x.close()
+    ref.close()
+    snap.close()
+
+
+def test_literal_reference_statistical_agreement():
+    """Against the reference as shipped (glibc libm): no per-sample exactness is possible in
+    principle (libm rounding), but at matched seeds the images must agree to ~1e-6."""
+    snap, cam, opt, ref, r = _setup("cornell", "wavefront", size=(128, 128), flavour="literal")
+    out = np.zeros((opt.height, opt.width, 4), np.float32)
+    for _ in range(8):
+        r.Render(cam, opt, out)
+    oracle = ref.render_seeded(0, 8, nthreads=8)
+    rel = np.linalg.norm((out - oracle).astype(np.float64)) / np.linalg.norm(oracle.astype(np.float64))
+    assert rel <= 1e-4, rel
+    r.close()
+    ref.close()
+    snap.close()

@@ -1,0 +1,178 @@
+"""tinsel_b200 -- B200-native wavefront path tracer behind tinsel's Renderer interface.
+
+This package is the Python-side host mirror used by the tests and bench.py: it loads the
+in-tree C-ABI library (tinsel_b200/libtinsel_b200.so: hand-written sm_100a kernels + host
+runtime, built by tinsel_b200/build.py) and wraps it in a `Renderer` with the reference's
+`Init(width, height)` / `Render(camera, options, output)` shape (src/render.h:66-73).
+There is no CPU fallback: if the library or a CUDA device is missing, creation fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import Camera, Options, Scene, Stats  # noqa: F401
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libtinsel_b200.so")
+ROOT = os.path.dirname(_PKG)
+SCENE_DIR = os.path.join(ROOT, "scenes")
+
+_lib = None
+
+
+class TinselB200Error(RuntimeError):
+    pass
+
+
+def load_library():
+    """Loads libtinsel_b200.so (never builds implicitly: use tinsel_b200.build.build_native)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TinselB200Error(
+            "native library %s is missing: run `python -m tinsel_b200.build` (needs nvcc); "
+            "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    f32p = C.POINTER(C.c_float)
+    lib.tb200_create.restype = C.c_void_p
+    lib.tb200_create.argtypes = [C.POINTER(Scene), C.c_int]
+    lib.tb200_init.restype = C.c_int
+    lib.tb200_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.tb200_render.restype = C.c_int
+    lib.tb200_render.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), f32p]
+    lib.tb200_render_device.restype = C.c_int
+    lib.tb200_render_device.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), C.c_int, C.c_int, C.c_int]
+    lib.tb200_device_accumulator.restype = C.c_void_p
+    lib.tb200_device_accumulator.argtypes = [C.c_void_p]
+    lib.tb200_read_accumulator.restype = C.c_int
+    lib.tb200_read_accumulator.argtypes = [C.c_void_p, f32p]
+    lib.tb200_trace_frame.restype = C.c_int
+    lib.tb200_trace_frame.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), C.c_int, f32p, f32p]
+    lib.tb200_set_frame.restype = None
+    lib.tb200_set_frame.argtypes = [C.c_void_p, C.c_int]
+    lib.tb200_get_stats.restype = None
+    lib.tb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.tb200_destroy.restype = None
+    lib.tb200_destroy.argtypes = [C.c_void_p]
+    lib.tb200_last_error.restype = C.c_char_p
+    lib.tb200_last_error.argtypes = []
+    abi.declare_snapshot_api(lib)
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load_library().tb200_last_error().decode()
+
+
+def sample_seed(pixel, frame):
+    return load_library().tb200_sample_seed(pixel, frame)
+
+
+def scene_path(name):
+    return os.path.join(SCENE_DIR, name + ".tsnap")
+
+
+class Snapshot:
+    """A .tsnap scene snapshot: tb200_scene + the camera and options the .tin file specified."""
+
+    def __init__(self, path):
+        self.lib = load_library()
+        self.h = self.lib.tb200_snapshot_load(path.encode())
+        if not self.h:
+            raise TinselB200Error("cannot load snapshot %s: %s" % (path, last_error()))
+        self.path = path
+
+    @property
+    def scene(self):
+        return self.lib.tb200_snapshot_scene(self.h)
+
+    @property
+    def camera(self):
+        return abi.copy_struct(self.lib.tb200_snapshot_camera(self.h).contents)
+
+    @property
+    def options(self):
+        return abi.copy_struct(self.lib.tb200_snapshot_options(self.h).contents)
+
+    def close(self):
+        if self.h:
+            self.lib.tb200_snapshot_free(self.h)
+            self.h = None
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Renderer:
+    """Host mirror of tinsel's `Renderer` (src/render.h:66-73) over the C ABI.
+
+    Renderer(scene)            <-> CreateGpuWavefrontRenderer(const Scene*)
+    Init(width, height)        <-> Renderer::Init
+    Render(camera, options, o) <-> Renderer::Render: adds one sample per pixel, `o` (H,W,4 float32)
+                                   receives the running sums (sum w*rgb, sum w)
+    """
+
+    def __init__(self, scene, device=0):
+        self.lib = load_library()
+        self.h = self.lib.tb200_create(scene, device)
+        if not self.h:
+            raise TinselB200Error("tb200_create failed: " + last_error())
+        self.width = self.height = 0
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TinselB200Error("%s failed: %s" % (what, last_error()))
+
+    def Init(self, width, height):
+        self._check(self.lib.tb200_init(self.h, width, height), "tb200_init")
+        self.width, self.height = width, height
+
+    def Render(self, camera, options, output):
+        assert output.dtype == np.float32 and output.flags["C_CONTIGUOUS"]
+        assert output.size == options.width * options.height * 4
+        self._check(self.lib.tb200_render(self.h, C.byref(camera), C.byref(options), _fp(output)), "tb200_render")
+
+    # batch / device-resident extensions (not part of the reference interface)
+    def render_device(self, camera, options, spp, first_row=0, num_rows=-1):
+        self._check(self.lib.tb200_render_device(self.h, C.byref(camera), C.byref(options), spp, first_row, num_rows),
+                    "tb200_render_device")
+
+    def read_accumulator(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        self._check(self.lib.tb200_read_accumulator(self.h, _fp(out)), "tb200_read_accumulator")
+        return out
+
+    def device_accumulator_ptr(self):
+        return self.lib.tb200_device_accumulator(self.h)
+
+    def trace_frame(self, camera, options, frame):
+        rad = np.empty((options.height, options.width, 3), np.float32)
+        ras = np.empty((options.height, options.width, 2), np.float32)
+        self._check(self.lib.tb200_trace_frame(self.h, C.byref(camera), C.byref(options), frame, _fp(rad), _fp(ras)),
+                    "tb200_trace_frame")
+        return rad, ras
+
+    def set_frame(self, frame):
+        self.lib.tb200_set_frame(self.h, frame)
+
+    def stats(self):
+        s = Stats()
+        self.lib.tb200_get_stats(self.h, C.byref(s))
+        return s
+
+    def close(self):
+        if self.h:
+            self.lib.tb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

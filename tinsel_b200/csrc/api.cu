@@ -1,0 +1,676 @@
+// api.cu -- host side of the C ABI (include/tinsel_b200.h): scene translation into the GPU
+// layout, accumulator management, frame sequencing, host read-back.
+//
+// Host arithmetic here restates reference *host-side* or *per-primitive-constant* expressions
+// (cited inline) and is compiled without contraction (-Xcompiler -ffp-contract=off, no fast-math)
+// so that it matches the reference's x86-64 build.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tb_kernels.cuh"
+
+const char* tb200_snapshot_error();   // snapshot.cpp
+
+namespace {
+
+thread_local std::string g_error;
+
+bool set_error(const std::string& what)
+{
+    g_error = what;
+    fprintf(stderr, "[tinsel_b200] %s\n", what.c_str());
+    return false;
+}
+
+#define TB_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                              \
+            return false;                                                                               \
+        }                                                                                               \
+    } while (0)
+
+template <typename T>
+bool upload(const std::vector<T>& host, T** dev, uint64_t* h2d, size_t padElems = 0)
+{
+    *dev = nullptr;
+    const size_t n = host.size() + padElems;
+    if (n == 0) return true;
+    TB_CUDA(cudaMalloc((void**)dev, n * sizeof(T)));
+    if (padElems) TB_CUDA(cudaMemset(*dev, 0, n * sizeof(T)));
+    if (!host.empty()) TB_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *h2d += host.size() * sizeof(T);
+    return true;
+}
+
+V3 hv3(const float* f) { return v3(f[0], f[1], f[2]); }
+
+Xf to_xf(const tb200_transform& t)
+{
+    Xf x;
+    x.p = hv3(t.p);
+    x.r = q4(t.r[0], t.r[1], t.r[2], t.r[3]);
+    x.s = t.s;
+    return x;
+}
+
+// Per-material constants.  The double intermediates are the reference's own:
+//   GetIndexOfRefraction  scene.h:72-78    2.0f/(1.0f-sqrtf(0.08*specular)) - 1.0f
+//   Cdlum                 disney.h:307     .3*r + .6*g + .1*b   (double, rounded to float)
+//   Ctint, Cspec0         disney.h:309-310 specular*.08 is a double product converted to Real
+//   clearcoat alpha       disney.h:387     Lerp(.1,.001,gloss) in double, converted to float
+DMaterial make_material(const tb200_material& m)
+{
+    DMaterial d;
+    d.emission = hv3(m.emission);
+    d.color = hv3(m.color);
+    d.absorption = hv3(m.absorption);
+    d.metallic = m.metallic;
+    d.subsurface = m.subsurface;
+    d.specular = m.specular;
+    d.roughness = m.roughness;
+    d.specularTint = m.specularTint;
+    d.clearcoat = m.clearcoat;
+    d.clearcoatGloss = m.clearcoatGloss;
+    d.transmission = m.transmission;
+
+    if (m.eta == 0.0f)
+        d.ior = 2.0f / (1.0f - sqrtf(float(0.08 * double(m.specular)))) - 1.0f;
+    else
+        d.ior = m.eta;
+
+    const float Cdlum = float(.3 * double(m.color[0]) + .6 * double(m.color[1]) + .1 * double(m.color[2]));
+    const V3 Cdlin = d.color;
+    const V3 Ctint = Cdlum > 0.0f ? Cdlin / Cdlum : v3s(1.0f);
+    const float spec08 = float(double(m.specular) * .08);
+    d.cspec0 = tb_lerp(spec08 * tb_lerp(v3s(1.0f), Ctint, m.specularTint), Cdlin, m.metallic);
+
+    d.sqrtColor = v3(sqrtf(m.color[0]), sqrtf(m.color[1]), sqrtf(m.color[2]));
+    d.alpha = tb_max(0.001f, m.roughness);
+
+    const float a = float(.1 + (.001 - .1) * double(m.clearcoatGloss));
+    d.gtr1Wide = (a >= 1) ? 1 : 0;
+    const float a2 = a * a;
+    d.gtr1A2m1 = a2 - 1;
+    d.gtr1PiLogA2 = TB_PI * logf(a2);
+    return d;
+}
+
+// BVHNode[] (bvh.h:9-19) -> BvhPair[]; see tb_scene.cuh.  Returns the root reference.
+uint32_t build_pairs(const tb200_bvh_node* nodes, int numNodes, std::vector<BvhPair>* out)
+{
+    out->clear();
+    if (numNodes <= 0) return TB_LEAF;   // never traversed: callers skip empty trees
+    std::vector<uint32_t> pairIndex(numNodes, 0xffffffffu);
+    uint32_t count = 0;
+    for (int i = 0; i < numNodes; ++i)
+        if (!(nodes[i].right_leaf >> 31)) pairIndex[i] = count++;
+    out->resize(count);
+    auto ref_of = [&](uint32_t idx) -> uint32_t {
+        const tb200_bvh_node& n = nodes[idx];
+        return (n.right_leaf >> 31) ? (TB_LEAF | n.left) : pairIndex[idx];
+    };
+    for (int i = 0; i < numNodes; ++i) {
+        if (nodes[i].right_leaf >> 31) continue;
+        const uint32_t li = nodes[i].left, ri = nodes[i].right_leaf & 0x7fffffffu;
+        const tb200_bvh_node& L = nodes[li];
+        const tb200_bvh_node& R = nodes[ri];
+        BvhPair p;
+        p.a = make_float4(L.lower[0], L.lower[1], L.lower[2], L.upper[0]);
+        p.b = make_float4(L.upper[1], L.upper[2], R.lower[0], R.lower[1]);
+        p.c = make_float4(R.lower[2], R.upper[0], R.upper[1], R.upper[2]);
+        p.left = ref_of(li);
+        p.right = ref_of(ri);
+        p.pad0 = p.pad1 = 0;
+        (*out)[pairIndex[i]] = p;
+    }
+    return ref_of(0);
+}
+
+// CameraSampler constructor, util.h:49-71, with Mat44(Transform) (maths.h:841-849), Mat33(Quat)
+// (maths.h:658-667) and MatrixMultiply<4,4,4> (maths.h:86-101: t = 0; t += a*b for k = 0..3).
+struct M44 {
+    float c[4][4];   // column major: c[col][row]
+};
+
+M44 mat_mul(const M44& a, const M44& b)
+{
+    M44 r;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float t = 0.0f;
+            for (int k = 0; k < 4; ++k) t += a.c[k][i] * b.c[j][k];
+            r.c[j][i] = t;
+        }
+    return r;
+}
+
+M44 mat_rows(float m11, float m12, float m13, float m14, float m21, float m22, float m23, float m24, float m31, float m32,
+             float m33, float m34, float m41, float m42, float m43, float m44)
+{
+    M44 m;
+    m.c[0][0] = m11; m.c[0][1] = m21; m.c[0][2] = m31; m.c[0][3] = m41;
+    m.c[1][0] = m12; m.c[1][1] = m22; m.c[1][2] = m32; m.c[1][3] = m42;
+    m.c[2][0] = m13; m.c[2][1] = m23; m.c[2][2] = m33; m.c[2][3] = m43;
+    m.c[3][0] = m14; m.c[3][1] = m24; m.c[3][2] = m34; m.c[3][3] = m44;
+    return m;
+}
+
+void camera_setup(const tb200_camera& cam, int width, int height, DCamera* out)
+{
+    Xf t;
+    t.p = hv3(cam.position);
+    t.r = q4(cam.rotation[0], cam.rotation[1], cam.rotation[2], cam.rotation[3]);
+    t.s = 1.0f;   // Transform(camera.position, camera.rotation), render.cpp:450-452
+
+    M44 c2w;
+    const V3 c0 = rotate(t.r, v3(1.0f, 0.0f, 0.0f)) * t.s;
+    const V3 c1 = rotate(t.r, v3(0.0f, 1.0f, 0.0f)) * t.s;
+    const V3 c2 = rotate(t.r, v3(0.0f, 0.0f, 1.0f)) * t.s;
+    const V3 c3 = t.p * t.s;
+    c2w.c[0][0] = c0.x; c2w.c[0][1] = c0.y; c2w.c[0][2] = c0.z; c2w.c[0][3] = 0.0f;
+    c2w.c[1][0] = c1.x; c2w.c[1][1] = c1.y; c2w.c[1][2] = c1.z; c2w.c[1][3] = 0.0f;
+    c2w.c[2][0] = c2.x; c2w.c[2][1] = c2.y; c2w.c[2][2] = c2.z; c2w.c[2][3] = 0.0f;
+    c2w.c[3][0] = c3.x; c2w.c[3][1] = c3.y; c2w.c[3][2] = c3.z; c2w.c[3][3] = 1.0f;
+
+    const M44 rasterToScreen = mat_rows(2.0f / width, 0.0f, 0.0f, -1.0f,
+                                        0.0f, -2.0f / height, 0.0f, 1.0f,
+                                        0.0f, 0.0f, 1.0f, 1.0f,
+                                        0.0f, 0.0f, 0.0f, 1.0f);
+    const float f = tanf(cam.fov * 0.5f);
+    const float aspect = float(width) / height;
+    const M44 screenToCamera = mat_rows(f * aspect, 0.0f, 0.0f, 0.0f,
+                                        0.0f, f, 0.0f, 0.0f,
+                                        0.0f, 0.0f, -1.0f, 0.0f,
+                                        0.0f, 0.0f, 0.0f, 1.0f);
+    const M44 r2w = mat_mul(mat_mul(c2w, screenToCamera), rasterToScreen);
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) out->r2w[c * 4 + r] = r2w.c[c][r];
+    out->origin = v3(c2w.c[3][0], c2w.c[3][1], c2w.c[3][2]);
+    out->shutterStart = cam.shutterStart;
+    out->shutterEnd = cam.shutterEnd;
+}
+
+}  // namespace
+
+struct tb200_renderer {
+    int device = 0;
+    int numSMs = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+
+    // device scene
+    DScene scene;
+    DPrim* dPrims = nullptr;
+    BvhPair* dScenePairs = nullptr;
+    DMesh* dMeshes = nullptr;
+    std::vector<void*> owned;   // every other device allocation
+
+    // film
+    int width = 0, height = 0;
+    float4* dAccum = nullptr;
+    float* dRadiance = nullptr;   // tb200_trace_frame scratch
+    float* dRaster = nullptr;
+    unsigned long long* dCounter = nullptr;
+    int frame = 0;
+
+    // host read-back
+    void* registered = nullptr;   // host pointer currently pinned with cudaHostRegister
+    size_t registeredBytes = 0;
+    void* lastOutput = nullptr;
+
+    int pipeline = 1;             // 0 = mega (validation), 1 = wavefront
+    tb200_stats stats;
+};
+
+namespace {
+
+void free_device(tb200_renderer* r)
+{
+    if (r->registered) {
+        cudaHostUnregister(r->registered);
+        r->registered = nullptr;
+    }
+    for (void* p : r->owned) cudaFree(p);
+    r->owned.clear();
+    cudaFree(r->dPrims);
+    cudaFree(r->dScenePairs);
+    cudaFree(r->dMeshes);
+    cudaFree(r->dAccum);
+    cudaFree(r->dRadiance);
+    cudaFree(r->dRaster);
+    cudaFree(r->dCounter);
+    r->dCounter = nullptr;
+    r->dPrims = nullptr;
+    r->dScenePairs = nullptr;
+    r->dMeshes = nullptr;
+    r->dAccum = nullptr;
+    r->dRadiance = r->dRaster = nullptr;
+}
+
+bool build_scene(tb200_renderer* r, const tb200_scene* s)
+{
+    uint64_t* h2d = &r->stats.h2dBytes;
+    memset(&r->scene, 0, sizeof(r->scene));
+
+    // meshes: pairs + pre-gathered triangles
+    std::vector<DMesh> meshes(s->numMeshes);
+    for (int m = 0; m < s->numMeshes; ++m) {
+        const tb200_mesh& g = s->meshes[m];
+        std::vector<BvhPair> pairs;
+        const uint32_t root = build_pairs(g.nodes, g.numNodes, &pairs);
+        const int numTris = g.numIndices / 3;
+        std::vector<float4> verts(size_t(numTris) * 3), norms(size_t(numTris) * 3);
+        for (int t = 0; t < numTris; ++t) {
+            const int i0 = g.indices[t * 3 + 0], i1 = g.indices[t * 3 + 1], i2 = g.indices[t * 3 + 2];
+            const float* a = g.positions + size_t(i0) * 3;
+            const float* b = g.positions + size_t(i1) * 3;
+            const float* c = g.positions + size_t(i2) * 3;
+            verts[size_t(t) * 3 + 0] = make_float4(a[0], a[1], a[2], b[0]);
+            verts[size_t(t) * 3 + 1] = make_float4(b[1], b[2], c[0], c[1]);
+            verts[size_t(t) * 3 + 2] = make_float4(c[2], 0.0f, 0.0f, 0.0f);
+            const float* n1 = g.normals + size_t(i0) * 3;
+            const float* n2 = g.normals + size_t(i1) * 3;
+            const float* n3 = g.normals + size_t(i2) * 3;
+            norms[size_t(t) * 3 + 0] = make_float4(n1[0], n1[1], n1[2], n2[0]);
+            norms[size_t(t) * 3 + 1] = make_float4(n2[1], n2[2], n3[0], n3[1]);
+            norms[size_t(t) * 3 + 2] = make_float4(n3[2], 0.0f, 0.0f, 0.0f);
+        }
+        std::vector<float> cdf(g.cdf, g.cdf + numTris);
+        BvhPair* dPairs;
+        float4 *dVerts, *dNorms;
+        float* dCdf;
+        if (!upload(pairs, &dPairs, h2d) || !upload(verts, &dVerts, h2d) || !upload(norms, &dNorms, h2d) ||
+            !upload(cdf, &dCdf, h2d))
+            return false;
+        r->owned.push_back(dPairs);
+        r->owned.push_back(dVerts);
+        r->owned.push_back(dNorms);
+        r->owned.push_back(dCdf);
+        meshes[m].pairs = dPairs;
+        meshes[m].triVerts = dVerts;
+        meshes[m].triNormals = dNorms;
+        meshes[m].cdf = dCdf;
+        meshes[m].numTris = numTris;
+        meshes[m].rootRef = root;
+    }
+    if (!upload(meshes, &r->dMeshes, h2d)) return false;
+
+    // primitives
+    std::vector<DPrim> prims(s->numPrimitives);
+    int numNee = s->sky.probeValid ? 1 : 0;
+    for (int i = 0; i < s->numPrimitives; ++i) {
+        const tb200_primitive& p = s->primitives[i];
+        DPrim& d = prims[i];
+        memset(&d, 0, sizeof(d));
+        d.start = to_xf(p.start);
+        d.end = to_xf(p.end);
+        d.isStatic = memcmp(&p.start, &p.end, sizeof(tb200_transform)) == 0;
+        // with start == end, Lerp(a,b,t) = a + (b-a)*t = a + 0*t is time independent
+        d.fixed = interpolate_transform(d.start, d.end, 0.0f);
+        d.type = p.type;
+        d.radius = p.radius;
+        memcpy(d.plane, p.plane, 16);
+        d.mesh = p.mesh;
+        d.lightSamples = p.lightSamples;
+        // PrimitiveArea, intersection.h:833-853
+        if (p.type == TB200_SPHERE)
+            d.area = 4.0f * TB_PI * p.radius * p.radius;
+        else if (p.type == TB200_MESH)
+            d.area = s->meshes[p.mesh].area * p.end.s;
+        else
+            d.area = 0.0f;
+        d.mat = make_material(p.material);
+        if (p.type == TB200_MESH && (p.mesh < 0 || p.mesh >= s->numMeshes)) return set_error("primitive references a missing mesh");
+        if (p.lightSamples > 0) numNee += p.lightSamples;
+    }
+    if (!upload(prims, &r->dPrims, h2d)) return false;
+
+    std::vector<BvhPair> scenePairs;
+    const uint32_t sceneRoot = build_pairs(s->bvhNodes, s->numBvhNodes, &scenePairs);
+    if (!upload(scenePairs, &r->dScenePairs, h2d)) return false;
+
+    DScene& sc = r->scene;
+    sc.prims = r->dPrims;
+    sc.numPrims = s->numPrimitives;
+    sc.pairs = r->dScenePairs;
+    sc.numPairs = (int)scenePairs.size();
+    sc.rootRef = sceneRoot;
+    sc.meshes = r->dMeshes;
+    sc.numMeshes = s->numMeshes;
+    sc.horizon = hv3(s->sky.horizon);
+    sc.zenith = hv3(s->sky.zenith);
+    sc.numNee = numNee;
+    if (s->sky.probeValid) {
+        const size_t n = size_t(s->sky.probeWidth) * s->sky.probeHeight;
+        // one element of slack after each table: ProbeSample's column search may land on
+        // col == width (probe.h:217-220) and read one past the last row
+        std::vector<float4> data(n);
+        memcpy(data.data(), s->sky.probeData, n * 16);
+        std::vector<float> pdfX(s->sky.pdfValuesX, s->sky.pdfValuesX + n), cdfX(s->sky.cdfValuesX, s->sky.cdfValuesX + n);
+        std::vector<float> pdfY(s->sky.pdfValuesY, s->sky.pdfValuesY + s->sky.probeHeight);
+        std::vector<float> cdfY(s->sky.cdfValuesY, s->sky.cdfValuesY + s->sky.probeHeight);
+        float4* dData;
+        float *dPdfX, *dCdfX, *dPdfY, *dCdfY;
+        if (!upload(data, &dData, h2d, 1) || !upload(pdfX, &dPdfX, h2d, 1) || !upload(cdfX, &dCdfX, h2d, 1) ||
+            !upload(pdfY, &dPdfY, h2d, 1) || !upload(cdfY, &dCdfY, h2d, 1))
+            return false;
+        r->owned.push_back(dData);
+        r->owned.push_back(dPdfX);
+        r->owned.push_back(dCdfX);
+        r->owned.push_back(dPdfY);
+        r->owned.push_back(dCdfY);
+        sc.probe.valid = 1;
+        sc.probe.width = s->sky.probeWidth;
+        sc.probe.height = s->sky.probeHeight;
+        sc.probe.data = dData;
+        sc.probe.pdfX = dPdfX;
+        sc.probe.cdfX = dCdfX;
+        sc.probe.pdfY = dPdfY;
+        sc.probe.cdfY = dCdfY;
+    }
+    return true;
+}
+
+bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_options* o, LaunchParams* P)
+{
+    if (!r->dAccum) return set_error("tb200_init has not been called");
+    if (o->width != r->width || o->height != r->height)
+        return set_error("options.width/height differ from the last tb200_init");
+    memset(P, 0, sizeof(*P));
+    P->scene = r->scene;
+    camera_setup(*camera, o->width, o->height, &P->camera);
+    P->film.width = o->width;
+    P->film.height = o->height;
+    P->film.filterType = o->filterType;
+    P->film.filterWidth = o->filterWidth;
+    P->film.filterFalloff = o->filterFalloff;
+    P->film.filterOffset = o->filterOffset;
+    P->film.clamp = o->clamp;
+    P->film.maxDepth = o->maxDepth;
+    P->accum = r->dAccum;
+    P->sampleCounter = r->dCounter;
+    P->firstRow = 0;
+    P->numRows = o->height;
+    return true;
+}
+
+bool launch_frames(tb200_renderer* r, LaunchParams& P)
+{
+    unsigned long long launches = 0;
+    TB_CUDA(cudaEventRecord(r->evStart, r->stream));
+    if (r->pipeline == 0)
+        launch_mega(P, r->stream, &launches);
+    else
+        launch_wavefront(P, r->numSMs, r->stream, &launches);
+    TB_CUDA(cudaEventRecord(r->evStop, r->stream));
+    TB_CUDA(cudaGetLastError());
+    r->stats.kernelLaunches += launches;
+    r->stats.samples += (uint64_t)P.numRows * P.film.width * P.numFrames;
+    return true;
+}
+
+bool finish_timing(tb200_renderer* r)
+{
+    TB_CUDA(cudaStreamSynchronize(r->stream));
+    float ms = 0.0f;
+    TB_CUDA(cudaEventElapsedTime(&ms, r->evStart, r->evStop));
+    r->stats.gpuMs = ms;
+    return true;
+}
+
+// device -> host copy of the accumulator.  A host buffer that is handed in twice in a row
+// (tinsel's main.cpp passes the same g_pixels every call, src/main.cpp:249) is pinned with
+// cudaHostRegister so the copy runs at PCIe speed instead of through the pageable path.
+bool read_back(tb200_renderer* r, float* output)
+{
+    const size_t bytes = size_t(r->width) * r->height * sizeof(float4);
+    if (output == r->lastOutput && r->registered != output) {
+        if (r->registered) {
+            cudaHostUnregister(r->registered);
+            r->registered = nullptr;
+        }
+        if (cudaHostRegister(output, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+            r->registered = output;
+            r->registeredBytes = bytes;
+        } else {
+            cudaGetLastError();   // not fatal: fall back to the pageable copy
+        }
+    }
+    r->lastOutput = output;
+    TB_CUDA(cudaMemcpyAsync(output, r->dAccum, bytes, cudaMemcpyDeviceToHost, r->stream));
+    TB_CUDA(cudaStreamSynchronize(r->stream));
+    r->stats.d2hBytes += bytes;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tb200_last_error(void)
+{
+    if (!g_error.empty()) return g_error.c_str();
+    return tb200_snapshot_error();
+}
+
+tb200_renderer* tb200_create(const tb200_scene* scene, int device)
+{
+    g_error.clear();
+    if (!scene) {
+        set_error("tb200_create: null scene");
+        return nullptr;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        set_error("tb200_create: no CUDA device available (this library has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= count) {
+        set_error("tb200_create: bad device ordinal");
+        return nullptr;
+    }
+    tb200_renderer* r = new tb200_renderer();
+    memset(&r->stats, 0, sizeof(r->stats));
+    r->device = device;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    cudaDeviceProp prop;
+    ok = ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+    if (ok) r->numSMs = prop.multiProcessorCount;
+    ok = ok && cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&r->evStart) == cudaSuccess && cudaEventCreate(&r->evStop) == cudaSuccess;
+    if (!ok) {
+        set_error(std::string("tb200_create: device setup failed: ") + cudaGetErrorString(cudaGetLastError()));
+        delete r;
+        return nullptr;
+    }
+    const char* pipe = getenv("TINSEL_B200_PIPELINE");
+    if (pipe && strcmp(pipe, "mega") == 0) r->pipeline = 0;
+    if (cudaMalloc((void**)&r->dCounter, sizeof(unsigned long long)) != cudaSuccess) {
+        set_error("tb200_create: counter allocation failed");
+        tb200_destroy(r);
+        return nullptr;
+    }
+    if (!build_scene(r, scene)) {
+        tb200_destroy(r);
+        return nullptr;
+    }
+    return r;
+}
+
+int tb200_init(tb200_renderer* r, int width, int height)
+{
+    if (!r || width <= 0 || height <= 0) {
+        set_error("tb200_init: bad arguments");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    if (r->registered) {
+        cudaHostUnregister(r->registered);   // the caller reallocates its buffer around Init (src/main.cpp:73-88)
+        cudaGetLastError();
+        r->registered = nullptr;
+    }
+    r->lastOutput = nullptr;
+    const size_t n = size_t(width) * height;
+    if (width != r->width || height != r->height || !r->dAccum) {
+        cudaFree(r->dAccum);
+        cudaFree(r->dRadiance);
+        cudaFree(r->dRaster);
+        r->dAccum = nullptr;
+        r->dRadiance = r->dRaster = nullptr;
+        if (cudaMalloc((void**)&r->dAccum, n * sizeof(float4)) != cudaSuccess) {
+            set_error("tb200_init: accumulator allocation failed");
+            return -1;
+        }
+        r->width = width;
+        r->height = height;
+    }
+    if (cudaMemsetAsync(r->dAccum, 0, n * sizeof(float4), r->stream) != cudaSuccess ||
+        cudaStreamSynchronize(r->stream) != cudaSuccess) {
+        set_error("tb200_init: accumulator clear failed");
+        return -1;
+    }
+    r->frame = 0;
+    r->stats.frames = 0;
+    return 0;
+}
+
+int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, float* output)
+{
+    if (!r || !camera || !options || !output) {
+        set_error("tb200_render: null argument");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    if (options->mode == TB200_MODE_COMPLEXITY) return 0;   // render.cpp:516-519
+    LaunchParams P;
+    if (!fill_params(r, camera, options, &P)) return -1;
+    if (options->mode == TB200_MODE_NORMALS) {
+        unsigned long long launches = 0;
+        cudaEventRecord(r->evStart, r->stream);
+        launch_normals(P, r->stream, &launches);
+        cudaEventRecord(r->evStop, r->stream);
+        r->stats.kernelLaunches += launches;
+    } else {
+        P.frame0 = r->frame;
+        P.numFrames = 1;
+        if (!launch_frames(r, P)) return -1;
+        r->frame += 1;
+        r->stats.frames += 1;
+    }
+    if (!read_back(r, output)) return -1;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, r->evStart, r->evStop);
+    r->stats.gpuMs = ms;
+    return 0;
+}
+
+int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int spp,
+                        int firstRow, int numRows)
+{
+    if (!r || !camera || !options || spp < 0) {
+        set_error("tb200_render_device: bad argument");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    if (options->mode != TB200_MODE_PATHTRACE) {
+        set_error("tb200_render_device: only ePathTrace is batched");
+        return -1;
+    }
+    LaunchParams P;
+    if (!fill_params(r, camera, options, &P)) return -1;
+    if (numRows >= 0) {
+        if (firstRow < 0 || firstRow + numRows > options->height) {
+            set_error("tb200_render_device: row range outside the image");
+            return -1;
+        }
+        P.firstRow = firstRow;
+        P.numRows = numRows;
+    }
+    P.frame0 = r->frame;
+    P.numFrames = spp;
+    if (spp > 0 && P.numRows > 0) {
+        if (!launch_frames(r, P)) return -1;
+        if (!finish_timing(r)) return -1;
+    }
+    r->frame += spp;
+    r->stats.frames += spp;
+    return 0;
+}
+
+float* tb200_device_accumulator(tb200_renderer* r) { return r ? (float*)r->dAccum : nullptr; }
+
+int tb200_read_accumulator(tb200_renderer* r, float* output)
+{
+    if (!r || !output || !r->dAccum) {
+        set_error("tb200_read_accumulator: bad argument");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    return read_back(r, output) ? 0 : -1;
+}
+
+int tb200_trace_frame(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int frame,
+                      float* radiance, float* raster)
+{
+    if (!r || !camera || !options || !radiance || !raster) {
+        set_error("tb200_trace_frame: null argument");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    LaunchParams P;
+    if (!fill_params(r, camera, options, &P)) return -1;
+    const size_t n = size_t(r->width) * r->height;
+    if (!r->dRadiance) {
+        if (cudaMalloc((void**)&r->dRadiance, n * 3 * sizeof(float)) != cudaSuccess ||
+            cudaMalloc((void**)&r->dRaster, n * 2 * sizeof(float)) != cudaSuccess) {
+            set_error("tb200_trace_frame: scratch allocation failed");
+            return -1;
+        }
+    }
+    P.frame0 = frame;
+    P.numFrames = 1;
+    P.outRadiance = r->dRadiance;
+    P.outRaster = r->dRaster;
+    const uint64_t samplesBefore = r->stats.samples;
+    if (!launch_frames(r, P)) return -1;
+    r->stats.samples = samplesBefore;
+    if (cudaMemcpyAsync(radiance, r->dRadiance, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, r->stream) != cudaSuccess ||
+        cudaMemcpyAsync(raster, r->dRaster, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, r->stream) != cudaSuccess ||
+        cudaStreamSynchronize(r->stream) != cudaSuccess) {
+        set_error(std::string("tb200_trace_frame: ") + cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    r->stats.d2hBytes += n * 5 * sizeof(float);
+    return 0;
+}
+
+void tb200_set_frame(tb200_renderer* r, int frame)
+{
+    if (r) r->frame = frame;
+}
+
+void tb200_get_stats(tb200_renderer* r, tb200_stats* out)
+{
+    if (r && out) *out = r->stats;
+}
+
+void tb200_destroy(tb200_renderer* r)
+{
+    if (!r) return;
+    cudaSetDevice(r->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    free_device(r);
+    if (r->evStart) cudaEventDestroy(r->evStart);
+    if (r->evStop) cudaEventDestroy(r->evStop);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+// tb_kernels.cuh -- kernel launch interface shared by api.cu (host side) and kernels.cu.
+#pragma once
+
+#include "tb_film.cuh"
+
+struct LaunchParams {
+    DScene scene;
+    DCamera camera;
+    DFilm film;
+    float4* accum;        // width*height running sums
+    unsigned long long* sampleCounter;   // per-renderer work counter of the wavefront kernel
+    int frame0;           // first frame (sample index per pixel)
+    int numFrames;        // frames to trace in this launch
+    int firstRow;         // pixel rows [firstRow, firstRow+numRows) are traced
+    int numRows;
+    // tb200_trace_frame outputs (nullptr in normal rendering)
+    float* outRadiance;   // 3 floats per pixel
+    float* outRaster;     // 2 floats per pixel
+};
+
+// one thread per (pixel, frame): the whole path in registers.  Validation / fallback pipeline.
+void launch_mega(const LaunchParams& p, cudaStream_t stream, unsigned long long* launchCount);
+// persistent CTA-resident wavefront pipeline (the product path)
+void launch_wavefront(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount);
+// eNormals mode (render.cpp:494-515)
+void launch_normals(const LaunchParams& p, cudaStream_t stream, unsigned long long* launchCount);

@@ -1,0 +1,334 @@
+// tb_scene.cuh -- GPU-side scene layout and the two-level closest-hit traversal.
+//
+// Layout (built on the host by api.cu from a tb200_scene):
+//   * DPrim[]     one record per Primitive (scene.h:142-159) with the per-primitive constants the
+//                 reference recomputes per ray hoisted out: the interpolated transform when
+//                 start==end (InterpolateTransform is then time-independent), PrimitiveArea,
+//                 GetIndexOfRefraction and the material-only subexpressions of BSDFEval.
+//   * BvhPair[]   the reference's BVHNode arrays (bvh.h:9-19) re-packed so that ONE interior
+//                 visit is ONE 64-byte record holding both children's boxes and references,
+//                 instead of three dependent 32-byte node fetches (self + 2 children,
+//                 intersection.h:694-708).  Tree topology, child order and visit order are
+//                 unchanged, so tie-breaks and the `tLeft < tmax` culling decisions are the
+//                 reference's, bit for bit.  A reference is (leaf << 31) | index.
+//   * tri verts   per-triangle pre-gathered positions (3 x float4, 48 B) replacing the
+//                 index -> vertex double indirection (intersection.h:638-644).
+#pragma once
+
+#include "tinsel_b200.h"
+#include "tb_math.cuh"
+
+#define TB_LEAF 0x80000000u
+#define TB_STACK 32  // the reference uses int stack[32] (intersection.h:688,759)
+
+struct __align__(16) BvhPair {
+    float4 a;   // L.lower.xyz, L.upper.x
+    float4 b;   // L.upper.yz, R.lower.xy
+    float4 c;   // R.lower.z, R.upper.xyz
+    uint32_t left, right;   // child references
+    uint32_t pad0, pad1;
+};
+
+struct DMaterial {
+    V3 emission;
+    V3 color;
+    V3 absorption;
+    float metallic, subsurface, specular, roughness, specularTint;
+    float clearcoat, clearcoatGloss, transmission;
+    // hoisted material-only subexpressions
+    float ior;            // Material::GetIndexOfRefraction, scene.h:72-78
+    V3 cspec0;            // disney.h:305-310
+    V3 sqrtColor;         // disney.h:358
+    float alpha;          // Max(0.001f, roughness), disney.h:139
+    float gtr1A2m1;       // a2-1 for the clearcoat GTR1, disney.h:61-63,387
+    float gtr1PiLogA2;    // kPi*logf(a2)
+    int gtr1Wide;         // a >= 1 -> GTR1 returns kInvPi
+};
+
+struct DMesh {
+    const BvhPair* pairs;
+    const float4* triVerts;     // 3 float4 per triangle: (ax ay az bx)(by bz cx cy)(cz - - -)
+    const float4* triNormals;   // same packing for the three vertex normals
+    const float* cdf;
+    int numTris;
+    uint32_t rootRef;
+};
+
+struct DPrim {
+    Xf start, end;
+    Xf fixed;             // InterpolateTransform(start,end,t) when isStatic
+    int isStatic;
+    int type;
+    float radius;
+    float plane[4];
+    int mesh;
+    int lightSamples;
+    float area;           // PrimitiveArea, intersection.h:833-853
+    DMaterial mat;
+};
+
+struct DProbe {
+    int valid, width, height;
+    const float4* data;
+    const float* pdfX;
+    const float* cdfX;
+    const float* pdfY;
+    const float* cdfY;
+};
+
+struct DScene {
+    const DPrim* prims;
+    int numPrims;
+    const BvhPair* pairs;     // scene-level BVH
+    int numPairs;
+    uint32_t rootRef;
+    const DMesh* meshes;
+    int numMeshes;
+    V3 horizon, zenith;
+    DProbe probe;
+    int numNee;               // shadow rays per surface hit: probe + sum(lightSamples)
+};
+
+struct Hit {
+    float t;
+    V3 n;        // FaceForward'ed (render.cpp:58)
+    int prim;    // -1: miss
+};
+
+TB_DEV Xf prim_transform(const DPrim& p, float time)
+{
+    if (p.isStatic) return p.fixed;
+    return interpolate_transform(p.start, p.end, time);
+}
+
+// IntersectRayAABBFast, intersection.h:373-397 (minf/maxf are the ternaries of :368-369)
+TB_DEV bool ray_aabb(V3 pos, V3 rcp, float lx, float ly, float lz, float ux, float uy, float uz, float& t)
+{
+    float l1 = (lx - pos.x) * rcp.x;
+    float l2 = (ux - pos.x) * rcp.x;
+    float lmin = tb_min(l1, l2);
+    float lmax = (l1 > l2) ? l1 : l2;
+
+    l1 = (ly - pos.y) * rcp.y;
+    l2 = (uy - pos.y) * rcp.y;
+    float mn = tb_min(l1, l2), mx = (l1 > l2) ? l1 : l2;
+    lmin = (mn > lmin) ? mn : lmin;
+    lmax = tb_min(mx, lmax);
+
+    l1 = (lz - pos.z) * rcp.z;
+    l2 = (uz - pos.z) * rcp.z;
+    mn = tb_min(l1, l2);
+    mx = (l1 > l2) ? l1 : l2;
+    lmin = (mn > lmin) ? mn : lmin;
+    lmax = tb_min(mx, lmax);
+
+    const bool hit = (lmax >= 0.f) & (lmax >= lmin);
+    if (hit) t = lmin;
+    return hit;
+}
+
+// IntersectRayTriTwoSided, intersection.h:117-145
+TB_DEV bool ray_tri(V3 p, V3 dir, V3 a, V3 b, V3 c, float& t, float& u, float& v, float& w, float& sign, V3& normal)
+{
+    const V3 ab = b - a;
+    const V3 ac = c - a;
+    const V3 n = cross(ab, ac);
+
+    const float d = dot(-dir, n);
+    const float ood = 1.0f / d;
+    const V3 ap = p - a;
+
+    t = dot(ap, n) * ood;
+    if (t < 0.0f) return false;
+
+    const V3 e = cross(-dir, ap);
+    v = dot(ac, e) * ood;
+    if (v < 0.0f || v > 1.0f) return false;
+    w = -dot(ab, e) * ood;
+    if (w < 0.0f || v + w > 1.0f) return false;
+
+    u = 1.0f - v - w;
+    normal = n;
+    sign = d;
+    return true;
+}
+
+struct MeshHit {
+    float t, u, v, w;
+    int tri;
+    V3 n;   // closestNormal = n*sign, unnormalised (intersection.h:658)
+};
+
+// IntersectRayMesh + MeshQuery, intersection.h:629-749
+TB_DEV bool ray_mesh(const DMesh& m, V3 origin, V3 dir, MeshHit& out)
+{
+    V3 rcp;
+    rcp.x = 1.0f / dir.x;
+    rcp.y = 1.0f / dir.y;
+    rcp.z = 1.0f / dir.z;
+
+    uint32_t stack[TB_STACK];
+    stack[0] = m.rootRef;
+    int count = 1;
+
+    float closestT = FLT_MAX;
+    float tmax = FLT_MAX;
+    out.tri = -1;
+
+    while (count) {
+        const uint32_t ref = stack[--count];
+        if (ref & TB_LEAF) {
+            const uint32_t i = ref & ~TB_LEAF;
+            const float4 q0 = __ldg(&m.triVerts[i * 3 + 0]);
+            const float4 q1 = __ldg(&m.triVerts[i * 3 + 1]);
+            const float4 q2 = __ldg(&m.triVerts[i * 3 + 2]);
+            float t, u, v, w, sign;
+            V3 n;
+            if (ray_tri(origin, dir, v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), v3(q1.z, q1.w, q2.x), t, u, v, w, sign, n)) {
+                if (t > 0.0f && t < closestT) {
+                    closestT = t;
+                    out.u = u;
+                    out.v = v;
+                    out.w = w;
+                    out.tri = (int)i;
+                    out.n = n * sign;
+                }
+            }
+            tmax = closestT;  // "truncate ray", intersection.h:700
+        } else {
+            const BvhPair* pr = &m.pairs[ref];
+            const float4 a = __ldg(&pr->a), b = __ldg(&pr->b), c = __ldg(&pr->c);
+            const uint2 kids = __ldg(reinterpret_cast<const uint2*>(&pr->left));
+            float tLeft, tRight;
+            const bool hitLeft = ray_aabb(origin, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft) && tLeft < tmax;
+            const bool hitRight = ray_aabb(origin, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight) && tRight < tmax;
+            uint32_t left = kids.x, right = kids.y;
+            // "traverse closest first": only the indices swap, not the hit flags (intersection.h:716-727)
+            if (hitLeft && hitRight && (tLeft < tRight)) {
+                const uint32_t tmp = left;
+                left = right;
+                right = tmp;
+            }
+            if (hitLeft) stack[count++] = left;
+            if (hitRight) stack[count++] = right;
+        }
+    }
+    if (closestT < FLT_MAX) {
+        out.t = closestT;
+        return true;
+    }
+    return false;
+}
+
+// SolveQuadratic with a == 1 + IntersectRaySphere, intersection.h:30-83
+TB_DEV bool ray_sphere(V3 center, float radius, V3 o, V3 d, float& outT, V3& outN)
+{
+    const V3 q = o - center;
+    const float a = 1.0f;
+    const float b = 2.0f * dot(q, d);
+    const float c = dot(q, q) - (radius * radius);
+
+    const float disc = b * b - 4.0f * a * c;
+    if (disc < 0.0f) return false;   // the reference falls through with r == false and returns it
+
+    const float tt = -0.5f * (b + ((b < 0.0f) ? -1.0f : 1.0f) * sqrtf(disc));
+    float minT = tt / a;
+    float maxT = c / tt;
+    if (maxT < minT) { const float s = minT; minT = maxT; maxT = s; }   // Sort2
+
+    if (minT < 0.0f && maxT < 0.0f) return false;
+    if (minT < 0.0f && maxT > 0.0f) minT = maxT;
+
+    outN = normalize((o + d * minT) - center);
+    outT = minT;
+    return true;
+}
+
+// PrimitiveIntersect, intersection.h:951-1020.  wantNormal=false skips the vertex-normal
+// interpolation for shadow rays (SampleLights only reads t and the hit primitive).
+TB_DEV bool prim_intersect(const DScene& sc, const DPrim& p, V3 o, V3 d, float time, bool wantNormal, float& outT, V3& outN)
+{
+    if (p.type == TB200_PLANE) {
+        // IntersectRayPlane, intersection.h:85-99; Dot(Vec4,Vec4) adds plane.w*0 resp. plane.w*1
+        const float dd = p.plane[0] * d.x + p.plane[1] * d.y + p.plane[2] * d.z + p.plane[3] * 0.0f;
+        if (dd == 0.0f) return false;
+        const float t = -(p.plane[0] * o.x + p.plane[1] * o.y + p.plane[2] * o.z + p.plane[3] * 1.0f) / dd;
+        outT = t;
+        outN = v3(p.plane[0], p.plane[1], p.plane[2]);
+        return t > 0.0f;
+    }
+    const Xf xf = prim_transform(p, time);
+    if (p.type == TB200_SPHERE) {
+        return ray_sphere(xf.p, p.radius * xf.s, o, d, outT, outN);
+    }
+    // mesh
+    const V3 lo = inverse_transform_point(xf, o);
+    const V3 ld = inverse_transform_vector(xf, d);
+    const DMesh& m = sc.meshes[p.mesh];
+    MeshHit mh;
+    if (!ray_mesh(m, lo, ld, mh)) return false;
+    outT = mh.t;
+    if (wantNormal) {
+        const float4 q0 = __ldg(&m.triNormals[mh.tri * 3 + 0]);
+        const float4 q1 = __ldg(&m.triNormals[mh.tri * 3 + 1]);
+        const float4 q2 = __ldg(&m.triNormals[mh.tri * 3 + 2]);
+        const V3 n1 = v3(q0.x, q0.y, q0.z), n2 = v3(q0.w, q1.x, q1.y), n3 = v3(q1.z, q1.w, q2.x);
+        V3 smooth = mh.u * n1 + mh.v * n2 + mh.w * n3;
+        if (dot(smooth, mh.n) < 0.0f) smooth = smooth * -1.0f;
+        outN = safe_normalize(transform_vector(xf, smooth), mh.n);
+    }
+    return true;
+}
+
+// Trace + QueryBVH, render.cpp:17-62 + intersection.h:751-799: near-first DFS over the scene
+// BVH with NO closest-t culling; the callback keeps `t < minT && t > 0` (first found wins ties).
+TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNormal)
+{
+    V3 rcp;
+    rcp.x = 1.0f / d.x;
+    rcp.y = 1.0f / d.y;
+    rcp.z = 1.0f / d.z;
+
+    uint32_t stack[TB_STACK];
+    stack[0] = sc.rootRef;
+    int count = 1;
+
+    float minT = FLT_MAX;
+    int closest = -1;
+    V3 closestN = v3s(0.0f);
+
+    while (count) {
+        const uint32_t ref = stack[--count];
+        if (ref & TB_LEAF) {
+            const int index = (int)(ref & ~TB_LEAF);
+            float t;
+            V3 n = v3s(0.0f);
+            if (prim_intersect(sc, sc.prims[index], o, d, time, wantNormal, t, n)) {
+                if (t < minT && t > 0.0f) {
+                    minT = t;
+                    closest = index;
+                    closestN = n;
+                }
+            }
+        } else {
+            const BvhPair* pr = &sc.pairs[ref];
+            const float4 a = pr->a, b = pr->b, c = pr->c;
+            float tLeft, tRight;
+            const bool hitLeft = ray_aabb(o, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft);
+            const bool hitRight = ray_aabb(o, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight);
+            uint32_t left = pr->left, right = pr->right;
+            if (hitLeft && hitRight && (tLeft < tRight)) {
+                const uint32_t tmp = left;
+                left = right;
+                right = tmp;
+            }
+            if (hitLeft) stack[count++] = left;
+            if (hitRight) stack[count++] = right;
+        }
+    }
+    Hit h;
+    h.t = minT;
+    h.prim = closest;
+    h.n = face_forward(closestN, -d);
+    return h;
+}
