@@ -158,3 +158,92 @@ class RefScene:
         if self.h:
             self.lib.ref_destroy(self.h)
             self.h = None
+
+
+# ---- the CPU restatement (oracle/libtinsel_oracle.so) ---------------------------------------------
+
+PORT_PATH = os.path.join(ROOT, "oracle", "libtinsel_oracle.so")
+_port = None
+
+
+def have_port():
+    return os.path.exists(PORT_PATH)
+
+
+def load_port():
+    global _port
+    if _port is not None:
+        return _port
+    lib = C.CDLL(PORT_PATH)
+    lib.oracle_create.restype = C.c_void_p
+    lib.oracle_create.argtypes = [C.POINTER(abi.Scene)]
+    lib.oracle_destroy.argtypes = [C.c_void_p]
+    lib.oracle_render_seeded.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.POINTER(abi.Options), C.c_int, C.c_int, _f32p, C.c_int]
+    lib.oracle_trace_frame.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.POINTER(abi.Options), C.c_int, _f32p, _f32p, C.c_int]
+    lib.oracle_render_normals.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.POINTER(abi.Options), _f32p]
+    lib.oracle_random_u32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint32)]
+    lib.oracle_random_f32.argtypes = [C.c_int, C.c_int, _f32p]
+    lib.oracle_material_ior.restype = C.c_float
+    lib.oracle_material_ior.argtypes = [C.POINTER(abi.Material)]
+    lib.oracle_bsdf_eval.argtypes = [C.POINTER(abi.Material), C.c_float, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p]
+    lib.oracle_bsdf_sample.argtypes = [C.POINTER(abi.Material), C.c_float, C.c_float, _f32p, _f32p, C.c_int, _f32p, _f32p,
+                                       C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+    lib.oracle_generate_ray.argtypes = [C.POINTER(abi.Camera), C.c_int, C.c_int, C.c_float, C.c_float, _f32p, _f32p]
+    lib.oracle_filter_eval.restype = C.c_float
+    lib.oracle_filter_eval.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+    lib.oracle_trace.restype = C.c_int
+    lib.oracle_trace.argtypes = [C.c_void_p, _f32p, _f32p, C.c_float, _f32p, _f32p]
+    lib.oracle_probe_sample.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p]
+    lib.oracle_sky_eval.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
+    lib.oracle_primitive_sample.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, _f32p, _f32p, _f32p]
+    abi.declare_snapshot_api(lib)
+    _port = lib
+    return lib
+
+
+class PortScene:
+    """The CPU restatement over a tb200_scene (from a snapshot or any tb200_scene view)."""
+
+    def __init__(self, scene_ptr, camera, options, keepalive=None):
+        self.lib = load_port()
+        self.h = C.c_void_p(self.lib.oracle_create(scene_ptr))
+        self.camera = abi.copy_struct(camera)
+        self.options = abi.copy_struct(options)
+        self._keep = keepalive
+
+    @classmethod
+    def from_snapshot(cls, path):
+        lib = load_port()
+        h = lib.tb200_snapshot_load(path.encode())
+        if not h:
+            raise RuntimeError("cannot load " + path)
+        scene = lib.tb200_snapshot_scene(h)
+        return cls(scene, lib.tb200_snapshot_camera(h).contents, lib.tb200_snapshot_options(h).contents, keepalive=h)
+
+    def set_size(self, w, h):
+        self.options.width, self.options.height = w, h
+
+    def render_seeded(self, frame0, nframes, nthreads=1, out=None):
+        o = self.options
+        if out is None:
+            out = np.zeros((o.height, o.width, 4), np.float32)
+        self.lib.oracle_render_seeded(self.h, C.byref(self.camera), C.byref(o), frame0, nframes, _fp(out), nthreads)
+        return out
+
+    def trace_frame(self, frame, nthreads=1):
+        o = self.options
+        rad = np.zeros((o.height, o.width, 3), np.float32)
+        ras = np.zeros((o.height, o.width, 2), np.float32)
+        self.lib.oracle_trace_frame(self.h, C.byref(self.camera), C.byref(o), frame, _fp(rad), _fp(ras), nthreads)
+        return rad, ras
+
+    def render_normals(self):
+        o = self.options
+        out = np.zeros((o.height, o.width, 4), np.float32)
+        self.lib.oracle_render_normals(self.h, C.byref(self.camera), C.byref(o), _fp(out))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_destroy(self.h)
+            self.h = None
