@@ -178,6 +178,22 @@ int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
 int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options,
                         int spp, int firstRow, int numRows);
 
+/* Image-plane sharding across GPUs: this renderer traces only the 4-pixel-high tile rows t with
+ * t % numShards == shard (interleaved for load balance).  Every sample is traced by exactly one
+ * shard with the same per-(pixel,frame) seed, so the sum over shards of the accumulators equals
+ * the unsharded image up to fp32 summation order.  Default: shard 0 of 1. */
+int tb200_set_shard(tb200_renderer* r, int shard, int numShards);
+
+/* Launch all work of this renderer on a caller-owned CUDA stream (a cudaStream_t passed as void*),
+ * e.g. torch's current stream, so that the caller's own events bracket it.  NULL restores the
+ * renderer's private stream. */
+int tb200_set_stream(tb200_renderer* r, void* cudaStream);
+
+/* Accumulate into caller-owned DEVICE memory (width*height*4 floats, e.g. a torch tensor that is
+ * then reduced with NCCL) instead of the renderer's own buffer.  Call after tb200_init; NULL
+ * switches back.  The caller zeroes its buffer. */
+int tb200_bind_accumulator(tb200_renderer* r, float* deviceAccum);
+
 /* Device pointer of the accumulator (width*height*4 floats) so that callers can reduce it
  * across GPUs (NCCL) without a host round trip.  Valid until the next tb200_init/destroy. */
 float* tb200_device_accumulator(tb200_renderer* r);

@@ -29,6 +29,17 @@
 #include "tb200_detmath.h"
 #include "tinsel_b200.h"
 
+// Optional work counters (-DTB_ORACLE_COUNT, built as libtinsel_oracle_count.so): the inputs of the
+// ALGORITHMIC-bytes formula of SURVEY.md 8(d), counted on the reference traversal order.
+enum { C_VINT, C_TTRI, C_TPRIM, C_HMESH, C_HIT, C_NEE_BYTES, C_PROBE_BYTES, C_MISS_BYTES, C_FB_PIXELS, C_RAYS, C_SAMPLES, C_NUM };
+#ifdef TB_ORACLE_COUNT
+#include <atomic>
+static std::atomic<unsigned long long> g_counters[C_NUM];
+#define COUNT(which, n) g_counters[which].fetch_add((unsigned long long)(n), std::memory_order_relaxed)
+#else
+#define COUNT(which, n) ((void)0)
+#endif
+
 namespace {
 
 struct vec3 {
@@ -196,6 +207,7 @@ bool mesh_closest(const tb200_mesh& m, vec3 o, vec3 d, mesh_hit& out)
     while (count) {
         const tb200_bvh_node& node = m.nodes[stack[--count]];
         if (node_is_leaf(node)) {
+            COUNT(C_TTRI, 1);
             int i = (int)node.left;
             int i0 = m.indices[i * 3 + 0], i1 = m.indices[i * 3 + 1], i2 = m.indices[i * 3 + 2];
             float t, u, v, w, sign;
@@ -212,6 +224,7 @@ bool mesh_closest(const tb200_mesh& m, vec3 o, vec3 d, mesh_hit& out)
             }
             tmax = closest;
         } else {
+            COUNT(C_VINT, 1);
             uint32_t li = node.left, ri = node_right(node);
             const tb200_bvh_node& L = m.nodes[li];
             const tb200_bvh_node& R = m.nodes[ri];
@@ -275,6 +288,7 @@ bool prim_hit(const tb200_scene& sc, const tb200_primitive& p, vec3 o, vec3 d, f
     vec3 lo = xf_inv_point(xf, o), ld = xf_inv_vector(xf, d);
     mesh_hit mh;
     if (!mesh_closest(m, lo, ld, mh)) return false;
+    COUNT(C_HMESH, 1);
     int i0 = m.indices[mh.tri * 3 + 0], i1 = m.indices[mh.tri * 3 + 1], i2 = m.indices[mh.tri * 3 + 2];
     vec3 n1 = from(m.normals + 3 * i0), n2 = from(m.normals + 3 * i1), n3 = from(m.normals + 3 * i2);
     vec3 smooth = add(add(scale(n1, mh.u), scale(n2, mh.v)), scale(n3, mh.w));
@@ -293,6 +307,7 @@ struct hit_t {
 // Trace + QueryBVH, render.cpp:17-62, intersection.h:751-799
 hit_t closest_hit(const tb200_scene& sc, vec3 o, vec3 d, float time)
 {
+    COUNT(C_RAYS, 1);
     vec3 rcp = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int stack[32];
     stack[0] = 0;
@@ -303,6 +318,7 @@ hit_t closest_hit(const tb200_scene& sc, vec3 o, vec3 d, float time)
     while (count) {
         const tb200_bvh_node& node = sc.bvhNodes[stack[--count]];
         if (node_is_leaf(node)) {
+            COUNT(C_TPRIM, 1);
             float t;
             vec3 n = splat(0.0f);
             if (prim_hit(sc, sc.primitives[node.left], o, d, time, t, n)) {
@@ -313,6 +329,7 @@ hit_t closest_hit(const tb200_scene& sc, vec3 o, vec3 d, float time)
                 }
             }
         } else {
+            COUNT(C_VINT, 1);
             uint32_t li = node.left, ri = node_right(node);
             const tb200_bvh_node& L = sc.bvhNodes[li];
             const tb200_bvh_node& R = sc.bvhNodes[ri];
@@ -576,6 +593,12 @@ void probe_sample(const tb200_sky& s, vec3& dir, vec3& color, float& pdf, rng_t&
 {
     float r1 = rng_f(rng), r2 = rng_f(rng);
     int W = s.probeWidth, H = s.probeHeight;
+    {
+        int lw = 0, lh = 0;
+        while ((1 << lw) < W) ++lw;
+        while ((1 << lh) < H) ++lh;
+        COUNT(C_PROBE_BYTES, 4 * (lw + lh) + 24);
+    }
     int row = lower_bound(s.cdfValuesY, 0, H, r1);
     int col = lower_bound(s.cdfValuesX, row * W, (row + 1) * W, r2) - row * W;
     color = from(s.probeData + 4 * (size_t)(row * W + col));
@@ -673,6 +696,15 @@ vec3 sample_lights(const tb200_scene& sc, const tb200_primitive& surf, float eta
         for (int s = 0; s < numSamples; ++s) {
             vec3 lightPos, lightNormal;
             prim_sample(sc, light, time, lightPos, lightNormal, rng);
+            {
+                int extra = 0;
+                if (light.type == TB200_MESH) {
+                    int ntri = sc.meshes[light.mesh].numIndices / 3, l2 = 0;
+                    while ((1 << l2) < ntri) ++l2;
+                    extra = 4 * l2 + 84;
+                }
+                COUNT(C_NEE_BYTES, 136 + extra);
+            }
             vec3 wi = sub(lightPos, p);
             float dSq = dot3(wi, wi);
             wi = divs(wi, sqrtf(dSq));
@@ -710,6 +742,7 @@ vec3 path_trace(const tb200_scene& sc, vec3 origin, vec3 dir, float time, int ma
     for (int i = 0; i < maxDepth; ++i) {
         hit_t h = closest_hit(sc, ro, rd, time);
         if (h.prim >= 0) {
+            COUNT(C_HIT, 1);
             const tb200_primitive& prim = sc.primitives[h.prim];
             float outEta;
             vec3 outAbs;
@@ -756,8 +789,10 @@ vec3 path_trace(const tb200_scene& sc, vec3 origin, vec3 dir, float time, int ma
             rd = bdir;
             ro = add(p, scale(face_fwd(n, bdir), RAY_EPS));
         } else {
+            COUNT(C_MISS_BYTES, sc.sky.probeValid ? 16 : 0);
             float weight = 1.0f;
             if (sc.sky.probeValid && i > 0 && rayType != SPECULAR) {
+                COUNT(C_MISS_BYTES, 8);
                 float skyPdf = probe_pdf(sc.sky, rd);
                 float cbsdf = 1.0f / 2, csky = 1.0f / 2;
                 weight = cbsdf * bsdfPdf / (cbsdf * bsdfPdf + csky * skyPdf);
@@ -825,8 +860,10 @@ void add_sample(const tb200_options& o, float* out, int W, int H, float rx, floa
     vec3 c = sample;
     float l = len3(sample);
     if (l > o.clamp) c = scale(sample, o.clamp / l);   // ClampLength, maths.h:1577-1589
+    COUNT(C_SAMPLES, 1);
     for (int x = sx; x <= ex; ++x)
         for (int y = sy; y <= ey; ++y) {
+            COUNT(C_FB_PIXELS, 1);
             float w = 1.0f;
             float* px = out + 4 * ((size_t)y * W + x);
             if (o.filterType == TB200_FILTER_GAUSSIAN) {
@@ -879,6 +916,22 @@ void parallel_bands(int H, int nthreads, F body)
 extern "C" {
 
 void* oracle_create(const tb200_scene* scene) { return new Oracle{scene}; }
+
+// work counters since the last reset (all zero unless built with -DTB_ORACLE_COUNT)
+int oracle_counters(unsigned long long* out, int reset)
+{
+#ifdef TB_ORACLE_COUNT
+    for (int i = 0; i < C_NUM; ++i) {
+        out[i] = g_counters[i].load();
+        if (reset) g_counters[i].store(0);
+    }
+    return C_NUM;
+#else
+    for (int i = 0; i < C_NUM; ++i) out[i] = 0;
+    (void)reset;
+    return 0;
+#endif
+}
 void oracle_destroy(void* h) { delete (Oracle*)h; }
 
 // Same contract as ref_render_seeded (oracle/ref_driver.cpp): adds frames into caller-zeroed sums.

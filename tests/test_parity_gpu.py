@@ -147,3 +147,25 @@ def test_literal_reference_statistical_agreement():
     r.close()
     ref.close()
     snap.close()
+
+
+def test_interleaved_shards_sum_to_full_image():
+    """Image-plane sharding (tb200_set_shard): the shard accumulators sum to the unsharded image."""
+    snap, cam, opt, ref, r = _setup("cornell", "wavefront", size=(100, 70))
+    r.render_device(cam, opt, 3)
+    full = r.read_accumulator()
+    total = np.zeros_like(full)
+    samples = 0
+    for shard in range(3):
+        rs = tb.Renderer(snap.scene)
+        rs.Init(opt.width, opt.height)
+        rs.set_shard(shard, 3)
+        rs.render_device(cam, opt, 3)
+        total += rs.read_accumulator()
+        samples += rs.stats().samples
+        rs.close()
+    assert samples == 3 * opt.width * opt.height
+    assert np.allclose(full, total, rtol=2e-6, atol=1e-6)
+    r.close()
+    ref.close()
+    snap.close()

@@ -45,6 +45,12 @@ def load_library():
     lib.tb200_render.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), f32p]
     lib.tb200_render_device.restype = C.c_int
     lib.tb200_render_device.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), C.c_int, C.c_int, C.c_int]
+    lib.tb200_set_shard.restype = C.c_int
+    lib.tb200_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.tb200_set_stream.restype = C.c_int
+    lib.tb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tb200_bind_accumulator.restype = C.c_int
+    lib.tb200_bind_accumulator.argtypes = [C.c_void_p, C.c_void_p]
     lib.tb200_device_accumulator.restype = C.c_void_p
     lib.tb200_device_accumulator.argtypes = [C.c_void_p]
     lib.tb200_read_accumulator.restype = C.c_int
@@ -141,6 +147,15 @@ class Renderer:
     def render_device(self, camera, options, spp, first_row=0, num_rows=-1):
         self._check(self.lib.tb200_render_device(self.h, C.byref(camera), C.byref(options), spp, first_row, num_rows),
                     "tb200_render_device")
+
+    def set_shard(self, shard, num_shards):
+        self._check(self.lib.tb200_set_shard(self.h, shard, num_shards), "tb200_set_shard")
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.lib.tb200_set_stream(self.h, C.c_void_p(cuda_stream_handle)), "tb200_set_stream")
+
+    def bind_accumulator(self, device_ptr):
+        self._check(self.lib.tb200_bind_accumulator(self.h, C.c_void_p(device_ptr)), "tb200_bind_accumulator")
 
     def read_accumulator(self, out=None):
         if out is None:

@@ -153,6 +153,9 @@ EXPORTS = [
     "tb200_init",
     "tb200_render",
     "tb200_render_device",
+    "tb200_set_shard",
+    "tb200_set_stream",
+    "tb200_bind_accumulator",
     "tb200_device_accumulator",
     "tb200_read_accumulator",
     "tb200_trace_frame",

@@ -4,6 +4,7 @@
 // Host arithmetic here restates reference *host-side* or *per-primitive-constant* expressions
 // (cited inline) and is compiled without contraction (-Xcompiler -ffp-contract=off, no fast-math)
 // so that it matches the reference's x86-64 build.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -201,7 +202,10 @@ void camera_setup(const tb200_camera& cam, int width, int height, DCamera* out)
 struct tb200_renderer {
     int device = 0;
     int numSMs = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // the stream work is launched on
+    cudaStream_t ownStream = nullptr;     // the renderer's private stream (default for `stream`)
+    int shard = 0, numShards = 1;
+    float4* boundAccum = nullptr;         // caller-owned accumulator (tb200_bind_accumulator)
     cudaEvent_t evStart = nullptr, evStop = nullptr;
 
     // device scene
@@ -393,10 +397,13 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     P->film.filterOffset = o->filterOffset;
     P->film.clamp = o->clamp;
     P->film.maxDepth = o->maxDepth;
-    P->accum = r->dAccum;
+    P->accum = r->boundAccum ? r->boundAccum : r->dAccum;
     P->sampleCounter = r->dCounter;
     P->firstRow = 0;
     P->numRows = o->height;
+    P->shard = r->shard;
+    P->numShards = r->numShards;
+    finalize_params(P);
     return true;
 }
 
@@ -404,14 +411,30 @@ bool launch_frames(tb200_renderer* r, LaunchParams& P)
 {
     unsigned long long launches = 0;
     TB_CUDA(cudaEventRecord(r->evStart, r->stream));
-    if (r->pipeline == 0)
-        launch_mega(P, r->stream, &launches);
-    else
-        launch_wavefront(P, r->numSMs, r->stream, &launches);
+    if (P.samplesPerFrame > 0) {
+        // slot records keep a 32-bit sample index: split very long jobs into several launches
+        const int framesPerLaunch = (int)std::max<unsigned long long>(1ull, 0x7fffffffull / P.samplesPerFrame);
+        const int frame0 = P.frame0, frames = P.numFrames;
+        for (int f = 0; f < frames; f += framesPerLaunch) {
+            P.frame0 = frame0 + f;
+            P.numFrames = std::min(framesPerLaunch, frames - f);
+            if (r->pipeline == 0)
+                launch_mega(P, r->stream, &launches);
+            else
+                launch_wavefront(P, r->numSMs, r->stream, &launches);
+        }
+        P.frame0 = frame0;
+        P.numFrames = frames;
+    }
     TB_CUDA(cudaEventRecord(r->evStop, r->stream));
     TB_CUDA(cudaGetLastError());
     r->stats.kernelLaunches += launches;
-    r->stats.samples += (uint64_t)P.numRows * P.film.width * P.numFrames;
+    {
+        // samples inside the image (tile padding excluded)
+        uint64_t rows = 0;
+        for (int t = P.shard; t * 4 < P.numRows; t += P.numShards) rows += (uint64_t)((P.numRows - t * 4) < 4 ? (P.numRows - t * 4) : 4);
+        r->stats.samples += rows * (uint64_t)P.film.width * (uint64_t)P.numFrames;
+    }
     return true;
 }
 
@@ -443,7 +466,7 @@ bool read_back(tb200_renderer* r, float* output)
         }
     }
     r->lastOutput = output;
-    TB_CUDA(cudaMemcpyAsync(output, r->dAccum, bytes, cudaMemcpyDeviceToHost, r->stream));
+    TB_CUDA(cudaMemcpyAsync(output, r->boundAccum ? r->boundAccum : r->dAccum, bytes, cudaMemcpyDeviceToHost, r->stream));
     TB_CUDA(cudaStreamSynchronize(r->stream));
     r->stats.d2hBytes += bytes;
     return true;
@@ -483,7 +506,8 @@ tb200_renderer* tb200_create(const tb200_scene* scene, int device)
     cudaDeviceProp prop;
     ok = ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
     if (ok) r->numSMs = prop.multiProcessorCount;
-    ok = ok && cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&r->ownStream, cudaStreamNonBlocking) == cudaSuccess;
+    r->stream = r->ownStream;
     ok = ok && cudaEventCreate(&r->evStart) == cudaSuccess && cudaEventCreate(&r->evStop) == cudaSuccess;
     if (!ok) {
         set_error(std::string("tb200_create: device setup failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -538,6 +562,7 @@ int tb200_init(tb200_renderer* r, int width, int height)
     }
     r->frame = 0;
     r->stats.frames = 0;
+    r->boundAccum = nullptr;
     return 0;
 }
 
@@ -592,6 +617,7 @@ int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb2
         }
         P.firstRow = firstRow;
         P.numRows = numRows;
+        finalize_params(&P);
     }
     P.frame0 = r->frame;
     P.numFrames = spp;
@@ -604,7 +630,44 @@ int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb2
     return 0;
 }
 
-float* tb200_device_accumulator(tb200_renderer* r) { return r ? (float*)r->dAccum : nullptr; }
+int tb200_set_shard(tb200_renderer* r, int shard, int numShards)
+{
+    if (!r || numShards < 1 || shard < 0 || shard >= numShards) {
+        set_error("tb200_set_shard: bad arguments");
+        return -1;
+    }
+    r->shard = shard;
+    r->numShards = numShards;
+    return 0;
+}
+
+int tb200_set_stream(tb200_renderer* r, void* cudaStream)
+{
+    if (!r) {
+        set_error("tb200_set_stream: null renderer");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    cudaStreamSynchronize(r->stream);
+    r->stream = cudaStream ? (cudaStream_t)cudaStream : r->ownStream;
+    return 0;
+}
+
+int tb200_bind_accumulator(tb200_renderer* r, float* deviceAccum)
+{
+    if (!r || !r->dAccum) {
+        set_error("tb200_bind_accumulator: call tb200_init first");
+        return -1;
+    }
+    r->boundAccum = (float4*)deviceAccum;
+    return 0;
+}
+
+float* tb200_device_accumulator(tb200_renderer* r)
+{
+    if (!r) return nullptr;
+    return (float*)(r->boundAccum ? r->boundAccum : r->dAccum);
+}
 
 int tb200_read_accumulator(tb200_renderer* r, float* output)
 {
@@ -667,6 +730,7 @@ void tb200_destroy(tb200_renderer* r)
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
     free_device(r);
+    r->stream = r->ownStream;
     if (r->evStart) cudaEventDestroy(r->evStart);
     if (r->evStop) cudaEventDestroy(r->evStop);
     if (r->stream) cudaStreamDestroy(r->stream);

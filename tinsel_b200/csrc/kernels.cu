@@ -5,6 +5,33 @@
 #include "tb_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
+// Work decomposition.  A launch covers numFrames x (the 8x4 pixel tiles of this shard inside the
+// row range).  Consecutive sample indices walk one tile (32 samples = one warp's worth of coherent
+// camera rays), then the next tile of the row, then the shard's next tile row.
+// ------------------------------------------------------------------------------------------------
+void finalize_params(LaunchParams* p)
+{
+    if (p->numShards < 1) p->numShards = 1;
+    p->tilesX = (p->film.width + 7) >> 3;
+    const int tileRowsAll = (p->numRows + 3) >> 2;
+    // tile rows t in [0, tileRowsAll) with t % numShards == shard
+    p->tileRows = tileRowsAll > p->shard ? (tileRowsAll - p->shard + p->numShards - 1) / p->numShards : 0;
+    p->samplesPerFrame = (unsigned long long)p->tilesX * (unsigned long long)p->tileRows * 32ull;
+}
+
+TB_DEV bool decode_sample(const LaunchParams& P, unsigned long long idx, int& px, int& py, int& frame)
+{
+    frame = P.frame0 + (int)(idx / P.samplesPerFrame);
+    const uint32_t local = (uint32_t)(idx % P.samplesPerFrame);
+    const uint32_t tile = local >> 5, in = local & 31u;
+    px = (int)((tile % (uint32_t)P.tilesX) * 8u + (in & 7u));
+    const int tileRow = (int)(tile / (uint32_t)P.tilesX) * P.numShards + P.shard;
+    const int ry = tileRow * 4 + (int)(in >> 3);
+    py = P.firstRow + ry;
+    return px < P.film.width && ry < P.numRows;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Shared per-sample prologue: seed Random per (pixel, frame), draw x,y,t in the oracle's order
 // (render.cpp:476-482), generate the camera ray.
 // ------------------------------------------------------------------------------------------------
@@ -46,14 +73,10 @@ TB_DEV void sample_end(const LaunchParams& P, int px, int py, float rasterX, flo
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_mega(LaunchParams P)
 {
-    const int W = P.film.width;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long perFrame = (long long)P.numRows * W;
-    if (idx >= perFrame * P.numFrames) return;
-    const int frame = P.frame0 + (int)(idx / perFrame);
-    const int local = (int)(idx % perFrame);
-    const int py = P.firstRow + local / W;
-    const int px = local % W;
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P.samplesPerFrame * (unsigned long long)P.numFrames) return;
+    int px, py, frame;
+    if (!decode_sample(P, idx, px, py, frame)) return;
 
     PathState ps;
     float rasterX, rasterY;
@@ -82,10 +105,10 @@ __global__ void __launch_bounds__(128) k_mega(LaunchParams P)
 
 void launch_mega(const LaunchParams& p, cudaStream_t stream, unsigned long long* launchCount)
 {
-    const long long total = (long long)p.numRows * p.film.width * p.numFrames;
-    if (total <= 0) return;
+    const unsigned long long total = p.samplesPerFrame * (unsigned long long)p.numFrames;
+    if (total == 0ull) return;
     const int block = 128;
-    const long long grid = (total + block - 1) / block;
+    const unsigned long long grid = (total + block - 1) / block;
     k_mega<<<(unsigned)grid, block, 0, stream>>>(p);
     if (launchCount) ++*launchCount;
 }

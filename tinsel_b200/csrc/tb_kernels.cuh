@@ -11,12 +11,19 @@ struct LaunchParams {
     unsigned long long* sampleCounter;   // per-renderer work counter of the wavefront kernel
     int frame0;           // first frame (sample index per pixel)
     int numFrames;        // frames to trace in this launch
-    int firstRow;         // pixel rows [firstRow, firstRow+numRows) are traced
+    int firstRow;         // pixel rows [firstRow, firstRow+numRows) are traced ...
     int numRows;
+    int shard, numShards; // ... restricted to 4-row tile rows t with t % numShards == shard
+    int tilesX;           // 8-pixel tile columns
+    int tileRows;         // tile rows owned by this shard inside the row range
+    unsigned long long samplesPerFrame;   // tilesX * tileRows * 32 (includes padding outside the image)
     // tb200_trace_frame outputs (nullptr in normal rendering)
     float* outRadiance;   // 3 floats per pixel
     float* outRaster;     // 2 floats per pixel
 };
+
+// fills tilesX / tileRows / samplesPerFrame from the row range and shard
+void finalize_params(LaunchParams* p);
 
 // one thread per (pixel, frame): the whole path in registers.  Validation / fallback pipeline.
 void launch_mega(const LaunchParams& p, cudaStream_t stream, unsigned long long* launchCount);

@@ -87,22 +87,6 @@ TB_DEV void wf_store(WfShared& S, int s, const PathState& ps, int bounce)
     S.flags[s] = 1u | ((uint32_t)ps.rayType << 1) | ((uint32_t)bounce << 8);
 }
 
-// launch-local sample index -> (px, py, frame).  Consecutive indices walk 8x4 pixel tiles so
-// that the 32 samples a warp regenerates together start as a coherent bundle of camera rays.
-TB_DEV bool wf_decode_sample(const LaunchParams& P, unsigned long long idx, int& px, int& py, int& frame)
-{
-    const int tilesX = (P.film.width + 7) >> 3;
-    const int tilesY = (P.numRows + 3) >> 2;
-    const unsigned long long perFrame = (unsigned long long)tilesX * tilesY * 32ull;
-    frame = P.frame0 + (int)(idx / perFrame);
-    const uint32_t local = (uint32_t)(idx % perFrame);
-    const uint32_t tile = local >> 5, in = local & 31u;
-    px = (int)((tile % tilesX) * 8 + (in & 7u));
-    const int ry = (int)((tile / tilesX) * 4 + (in >> 3));
-    py = P.firstRow + ry;
-    return px < P.film.width && ry < P.numRows;
-}
-
 // raster position of a sample: its first two RNG draws (render.cpp:476,481-482)
 TB_DEV void wf_raster_of(const LaunchParams& P, int px, int py, int frame, float& rx, float& ry)
 {
@@ -116,7 +100,7 @@ TB_DEV void wf_raster_of(const LaunchParams& P, int px, int py, int frame, float
 TB_DEV void wf_finish(const LaunchParams& P, WfShared& S, int s, V3 radiance)
 {
     int px, py, frame;
-    wf_decode_sample(P, S.sample[s] + 0ull, px, py, frame);
+    decode_sample(P, (unsigned long long)S.sample[s], px, py, frame);
     float rx, ry;
     wf_raster_of(P, px, py, frame, rx, ry);
     sample_end(P, px, py, rx, ry, radiance);
@@ -195,7 +179,7 @@ __global__ void __launch_bounds__(TB_WF_THREADS, 1) k_wavefront(LaunchParams P, 
                     if (!__any_sync(0xffffffffu, want)) break;
                     if (want && got) {
                         int px, py, frame;
-                        if (wf_decode_sample(P, idx, px, py, frame)) {
+                        if (decode_sample(P, idx, px, py, frame)) {
                             float rx, ry;
                             sample_begin(P, px, py, frame, ps, rx, ry);
                             S.sample[s] = (uint32_t)idx;
@@ -309,9 +293,7 @@ __global__ void __launch_bounds__(TB_WF_THREADS, 1) k_wavefront(LaunchParams P, 
 
 void launch_wavefront(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
 {
-    const int tilesX = (p.film.width + 7) >> 3;
-    const int tilesY = (p.numRows + 3) >> 2;
-    const unsigned long long total = (unsigned long long)tilesX * tilesY * 32ull * (unsigned long long)p.numFrames;
+    const unsigned long long total = p.samplesPerFrame * (unsigned long long)p.numFrames;
     if (total == 0ull) return;
     static bool configured = false;
     if (!configured) {
