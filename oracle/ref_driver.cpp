@@ -279,6 +279,11 @@ const tb200_scene* ref_scene(void* h) { return &((RefScene*)h)->xscene; }
 const tb200_camera* ref_camera(void* h) { return &((RefScene*)h)->xcamera; }
 const tb200_options* ref_options(void* h) { return &((RefScene*)h)->xoptions; }
 
+// the reference's own objects, for tests that hand them to the C++ plugin (tinsel_plugin.cpp)
+const void* ref_native_scene(void* h) { return &((RefScene*)h)->scene; }
+const void* ref_native_camera(void* h) { return &((RefScene*)h)->camera; }
+const void* ref_native_options(void* h) { return &((RefScene*)h)->options; }
+
 void ref_set_size(void* h, int width, int height)
 {
     RefScene* rs = (RefScene*)h;

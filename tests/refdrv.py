@@ -50,6 +50,9 @@ def load_ref(flavour="detmath"):
     lib.ref_camera.argtypes = [C.c_void_p]
     lib.ref_options.restype = C.POINTER(abi.Options)
     lib.ref_options.argtypes = [C.c_void_p]
+    for name in ("ref_native_scene", "ref_native_camera", "ref_native_options"):
+        getattr(lib, name).restype = C.c_void_p
+        getattr(lib, name).argtypes = [C.c_void_p]
     lib.ref_set_size.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.ref_set_mode.argtypes = [C.c_void_p, C.c_int]
     lib.ref_set_max_depth.argtypes = [C.c_void_p, C.c_int]

@@ -31,11 +31,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("TINSEL_B200_LIB", LIB_PATH)   # development: alternative builds of the same library
+    if not os.path.exists(path):
         raise TinselB200Error(
             "native library %s is missing: run `python -m tinsel_b200.build` (needs nvcc); "
-            "there is no CPU fallback" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+            "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
     f32p = C.POINTER(C.c_float)
     lib.tb200_create.restype = C.c_void_p
     lib.tb200_create.argtypes = [C.POINTER(Scene), C.c_int]

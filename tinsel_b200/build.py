@@ -47,13 +47,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force=False, verbose=False, extra_flags=()):
-    if not force and not needs_build():
+def build_native(force=False, verbose=False, extra_flags=(), out=None):
+    """out: alternative library name (development variants, selected with TINSEL_B200_LIB)."""
+    lib = os.path.join(PKG, out) if out else LIB
+    if not force and not out and not needs_build():
         return LIB
     objs = []
-    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    tag = (out or "default").replace(".", "_")
+    os.makedirs(os.path.join(PKG, "build", tag), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(PKG, "build", src + ".o")
+        obj = os.path.join(PKG, "build", tag, src + ".o")
         cmd = [_nvcc(), "-ccbin", _host_compiler(), *NVCC_FLAGS, *extra_flags, "-I", os.path.join(ROOT, "include"),
                "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if src.endswith(".cpp"):
@@ -63,14 +66,20 @@ def build_native(force=False, verbose=False, extra_flags=()):
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [_nvcc(), "-ccbin", _host_compiler(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs,
+    cmd = [_nvcc(), "-ccbin", _host_compiler(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *objs,
            "-lcudart"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    extra = [a for a in sys.argv[1:] if a not in ("-f", "-V")]
-    print(build_native(force="-f" in sys.argv, verbose="-V" in sys.argv, extra_flags=extra))
+    argv = sys.argv[1:]
+    out = None
+    if "--out" in argv:
+        i = argv.index("--out")
+        out = argv[i + 1]
+        del argv[i:i + 2]
+    extra = [a for a in argv if a not in ("-f", "-V")]
+    print(build_native(force="-f" in argv, verbose="-V" in argv, extra_flags=extra, out=out))

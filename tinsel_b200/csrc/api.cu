@@ -133,6 +133,38 @@ uint32_t build_pairs(const tb200_bvh_node* nodes, int numNodes, std::vector<BvhP
     return ref_of(0);
 }
 
+// Flat scene program for trace_closest() (tb_scene.cuh): the scene BVH's nodes in an order where
+// parents precede children.  Built only for scenes of at most 16 primitives (<= 31 nodes, one
+// bit each in the per-ray visited mask).
+void build_flat(const tb200_bvh_node* nodes, int numNodes, int numPrims, std::vector<FlatNode>* out)
+{
+    out->clear();
+    if (numNodes <= 0 || numNodes > 31 || numPrims > 16) return;
+    struct Item { uint32_t node; int parent; };
+    std::vector<Item> todo;
+    todo.push_back({0u, -1});
+    while (!todo.empty()) {
+        const Item it = todo.back();
+        todo.pop_back();
+        const tb200_bvh_node& n = nodes[it.node];
+        FlatNode f;
+        memcpy(f.lo, n.lower, 12);
+        memcpy(f.hi, n.upper, 12);
+        f.parent = it.parent < 0 ? 0 : it.parent;
+        const bool leaf = (n.right_leaf >> 31) != 0;
+        bool infinite = true;
+        for (int k = 0; k < 3; ++k) infinite = infinite && n.lower[k] <= -5.0e7f && n.upper[k] >= 5.0e7f;
+        f.info = (leaf ? 1 : 0) | (infinite ? 2 : 0) | (leaf ? int(n.left) << 8 : 0);
+        const int me = int(out->size());
+        out->push_back(f);
+        if (!leaf) {
+            todo.push_back({n.right_leaf & 0x7fffffffu, me});
+            todo.push_back({n.left, me});
+        }
+    }
+    if (out->size() > 31) out->clear();
+}
+
 // CameraSampler constructor, util.h:49-71, with Mat44(Transform) (maths.h:841-849), Mat33(Quat)
 // (maths.h:658-667) and MatrixMultiply<4,4,4> (maths.h:86-101: t = 0; t += a*b for k = 0..3).
 struct M44 {
@@ -212,6 +244,7 @@ struct tb200_renderer {
     DScene scene;
     DPrim* dPrims = nullptr;
     BvhPair* dScenePairs = nullptr;
+    FlatNode* dFlat = nullptr;
     DMesh* dMeshes = nullptr;
     std::vector<void*> owned;   // every other device allocation
 
@@ -244,6 +277,8 @@ void free_device(tb200_renderer* r)
     r->owned.clear();
     cudaFree(r->dPrims);
     cudaFree(r->dScenePairs);
+    cudaFree(r->dFlat);
+    r->dFlat = nullptr;
     cudaFree(r->dMeshes);
     cudaFree(r->dAccum);
     cudaFree(r->dRadiance);
@@ -344,6 +379,11 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
     sc.numPrims = s->numPrimitives;
     sc.pairs = r->dScenePairs;
     sc.numPairs = (int)scenePairs.size();
+    std::vector<FlatNode> flat;
+    if (!getenv("TINSEL_B200_NO_FLAT")) build_flat(s->bvhNodes, s->numBvhNodes, s->numPrimitives, &flat);
+    if (!upload(flat, &r->dFlat, h2d)) return false;
+    sc.flat = r->dFlat;
+    sc.numFlat = (int)flat.size();
     sc.rootRef = sceneRoot;
     sc.meshes = r->dMeshes;
     sc.numMeshes = s->numMeshes;
@@ -397,6 +437,13 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     P->film.filterOffset = o->filterOffset;
     P->film.clamp = o->clamp;
     P->film.maxDepth = o->maxDepth;
+    // Gaussian() is exactly +0 wherever expf(arg) < offset; keep a 1e-3 relative margin so the
+    // shortcut never depends on the last bits of expf (tb_film.cuh: filter_gaussian)
+    P->film.filterArgZero = -INFINITY;
+    if (o->filterOffset > 0.0f && o->filterOffset < 1.0f) {
+        const float a = (float)log((double)o->filterOffset * (1.0 - 1.0e-3));
+        if (tbm_expf(a) < o->filterOffset) P->film.filterArgZero = a;
+    }
     P->accum = r->boundAccum ? r->boundAccum : r->dAccum;
     P->sampleCounter = r->dCounter;
     P->firstRow = 0;

@@ -19,10 +19,13 @@ void finalize_params(LaunchParams* p)
     p->samplesPerFrame = (unsigned long long)p->tilesX * (unsigned long long)p->tileRows * 32ull;
 }
 
-TB_DEV bool decode_sample(const LaunchParams& P, unsigned long long idx, int& px, int& py, int& frame)
+// (launches are split on the host so that idx and samplesPerFrame fit 31 bits: 32-bit division)
+TB_DEV bool decode_sample(const LaunchParams& P, unsigned long long idx64, int& px, int& py, int& frame)
 {
-    frame = P.frame0 + (int)(idx / P.samplesPerFrame);
-    const uint32_t local = (uint32_t)(idx % P.samplesPerFrame);
+    const uint32_t idx = (uint32_t)idx64, spf = (uint32_t)P.samplesPerFrame;
+    const uint32_t f = idx / spf;
+    frame = P.frame0 + (int)f;
+    const uint32_t local = idx - f * spf;
     const uint32_t tile = local >> 5, in = local & 31u;
     px = (int)((tile % (uint32_t)P.tilesX) * 8u + (in & 7u));
     const int tileRow = (int)(tile / (uint32_t)P.tilesX) * P.numShards + P.shard;

@@ -16,6 +16,9 @@ struct DFilm {
     float filterWidth, filterFalloff, filterOffset;
     float clamp;
     int maxDepth;
+    // arguments below this give expf(arg) < offset by a wide margin, i.e. Gaussian() == +0 exactly
+    // (host: log(offset*(1-1e-3)); -inf disables the shortcut)
+    float filterArgZero;
 };
 
 // GenerateRay, util.h:73-79 with TransformPoint(Mat44, Vec3(x,y,0)), maths.h:923-930
@@ -31,7 +34,12 @@ TB_DEV void generate_ray(const DCamera& cam, float rx, float ry, V3& origin, V3&
 }
 
 // Filter::Gaussian, render.h:29-32 (offset is taken as handed in, never recomputed)
-TB_DEV float filter_gaussian(const DFilm& f, float x) { return tb_max(0.0f, tbm_expf(-f.filterFalloff * x * x) - f.filterOffset); }
+TB_DEV float filter_gaussian(const DFilm& f, float x)
+{
+    const float arg = -f.filterFalloff * x * x;
+    if (arg < f.filterArgZero) return 0.0f;   // Max(0, expf(arg) - offset) with expf(arg) < offset
+    return tb_max(0.0f, tbm_expf(arg) - f.filterOffset);
+}
 
 // one 16-byte vector reduction per touched pixel (sm_90+: red.global.add.v4.f32)
 TB_DEV void accum_add(float4* accum, int idx, float r, float g, float b, float w)

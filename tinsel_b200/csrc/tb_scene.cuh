@@ -19,6 +19,12 @@
 #include "tb_math.cuh"
 
 #define TB_LEAF 0x80000000u
+// the ordered scene walk is the rarely taken fallback of trace_closest(); out of line by default
+#ifdef TB_ORDERED_INLINE
+#define TB_ORDERED_ATTR static __device__ __forceinline__
+#else
+#define TB_ORDERED_ATTR static __device__ __noinline__
+#endif
 #define TB_STACK 32  // the reference uses int stack[32] (intersection.h:688,759)
 
 struct __align__(16) BvhPair {
@@ -87,6 +93,8 @@ struct DScene {
     V3 horizon, zenith;
     DProbe probe;
     int numNee;               // shadow rays per surface hit: probe + sum(lightSamples)
+    const struct FlatNode* flat;   // flat scene program (nullptr / numFlat == 0: use the ordered walk)
+    int numFlat;
 };
 
 struct Hit {
@@ -220,69 +228,80 @@ TB_DEV bool ray_mesh(const DMesh& m, V3 origin, V3 dir, MeshHit& out)
     return false;
 }
 
-// SolveQuadratic with a == 1 + IntersectRaySphere, intersection.h:30-83
-TB_DEV bool ray_sphere(V3 center, float radius, V3 o, V3 d, float& outT, V3& outN)
-{
-    const V3 q = o - center;
-    const float a = 1.0f;
-    const float b = 2.0f * dot(q, d);
-    const float c = dot(q, q) - (radius * radius);
+// PrimitiveIntersect, intersection.h:951-1020, split in two: prim_test() decides hit / t exactly
+// as the reference does, prim_normal() produces *outNormal for a recorded hit.  The reference
+// computes the normal of every candidate (no side effects); only the winner's is ever used, so
+// the traversals below call prim_normal() once, for the closest hit (and never for shadow rays:
+// SampleLights only reads t and the hit primitive).
+struct PrimHit {
+    float t;
+    int tri;
+    float u, v, w;
+    V3 gn;     // MeshQuery::closestNormal (n*sign, unnormalised)
+};
 
-    const float disc = b * b - 4.0f * a * c;
-    if (disc < 0.0f) return false;   // the reference falls through with r == false and returns it
-
-    const float tt = -0.5f * (b + ((b < 0.0f) ? -1.0f : 1.0f) * sqrtf(disc));
-    float minT = tt / a;
-    float maxT = c / tt;
-    if (maxT < minT) { const float s = minT; minT = maxT; maxT = s; }   // Sort2
-
-    if (minT < 0.0f && maxT < 0.0f) return false;
-    if (minT < 0.0f && maxT > 0.0f) minT = maxT;
-
-    outN = normalize((o + d * minT) - center);
-    outT = minT;
-    return true;
-}
-
-// PrimitiveIntersect, intersection.h:951-1020.  wantNormal=false skips the vertex-normal
-// interpolation for shadow rays (SampleLights only reads t and the hit primitive).
-TB_DEV bool prim_intersect(const DScene& sc, const DPrim& p, V3 o, V3 d, float time, bool wantNormal, float& outT, V3& outN)
+TB_DEV bool prim_test(const DScene& sc, const DPrim& p, V3 o, V3 d, float time, PrimHit& ph)
 {
     if (p.type == TB200_PLANE) {
         // IntersectRayPlane, intersection.h:85-99; Dot(Vec4,Vec4) adds plane.w*0 resp. plane.w*1
         const float dd = p.plane[0] * d.x + p.plane[1] * d.y + p.plane[2] * d.z + p.plane[3] * 0.0f;
         if (dd == 0.0f) return false;
         const float t = -(p.plane[0] * o.x + p.plane[1] * o.y + p.plane[2] * o.z + p.plane[3] * 1.0f) / dd;
-        outT = t;
-        outN = v3(p.plane[0], p.plane[1], p.plane[2]);
+        ph.t = t;
         return t > 0.0f;
     }
     const Xf xf = prim_transform(p, time);
     if (p.type == TB200_SPHERE) {
-        return ray_sphere(xf.p, p.radius * xf.s, o, d, outT, outN);
+        // SolveQuadratic with a == 1 + IntersectRaySphere, intersection.h:30-83
+        const V3 q = o - xf.p;
+        const float radius = p.radius * xf.s;
+        const float a = 1.0f;
+        const float b = 2.0f * dot(q, d);
+        const float c = dot(q, q) - (radius * radius);
+        const float disc = b * b - 4.0f * a * c;
+        if (disc < 0.0f) return false;   // the reference falls through with r == false and returns it
+        const float tt = -0.5f * (b + ((b < 0.0f) ? -1.0f : 1.0f) * sqrtf(disc));
+        float minT = tt / a;
+        float maxT = c / tt;
+        if (maxT < minT) { const float s = minT; minT = maxT; maxT = s; }   // Sort2
+        if (minT < 0.0f && maxT < 0.0f) return false;
+        if (minT < 0.0f && maxT > 0.0f) minT = maxT;
+        ph.t = minT;
+        return true;
     }
     // mesh
     const V3 lo = inverse_transform_point(xf, o);
     const V3 ld = inverse_transform_vector(xf, d);
-    const DMesh& m = sc.meshes[p.mesh];
     MeshHit mh;
-    if (!ray_mesh(m, lo, ld, mh)) return false;
-    outT = mh.t;
-    if (wantNormal) {
-        const float4 q0 = __ldg(&m.triNormals[mh.tri * 3 + 0]);
-        const float4 q1 = __ldg(&m.triNormals[mh.tri * 3 + 1]);
-        const float4 q2 = __ldg(&m.triNormals[mh.tri * 3 + 2]);
-        const V3 n1 = v3(q0.x, q0.y, q0.z), n2 = v3(q0.w, q1.x, q1.y), n3 = v3(q1.z, q1.w, q2.x);
-        V3 smooth = mh.u * n1 + mh.v * n2 + mh.w * n3;
-        if (dot(smooth, mh.n) < 0.0f) smooth = smooth * -1.0f;
-        outN = safe_normalize(transform_vector(xf, smooth), mh.n);
-    }
+    if (!ray_mesh(sc.meshes[p.mesh], lo, ld, mh)) return false;
+    ph.t = mh.t;
+    ph.tri = mh.tri;
+    ph.u = mh.u;
+    ph.v = mh.v;
+    ph.w = mh.w;
+    ph.gn = mh.n;
     return true;
+}
+
+TB_DEV V3 prim_normal(const DScene& sc, const DPrim& p, V3 o, V3 d, float time, const PrimHit& ph)
+{
+    if (p.type == TB200_PLANE) return v3(p.plane[0], p.plane[1], p.plane[2]);
+    const Xf xf = prim_transform(p, time);
+    if (p.type == TB200_SPHERE) return normalize((o + d * ph.t) - xf.p);   // intersection.h:76-79
+    const DMesh& m = sc.meshes[p.mesh];
+    const float4 q0 = __ldg(&m.triNormals[ph.tri * 3 + 0]);
+    const float4 q1 = __ldg(&m.triNormals[ph.tri * 3 + 1]);
+    const float4 q2 = __ldg(&m.triNormals[ph.tri * 3 + 2]);
+    const V3 n1 = v3(q0.x, q0.y, q0.z), n2 = v3(q0.w, q1.x, q1.y), n3 = v3(q1.z, q1.w, q2.x);
+    V3 smooth = ph.u * n1 + ph.v * n2 + ph.w * n3;
+    if (dot(smooth, ph.gn) < 0.0f) smooth = smooth * -1.0f;
+    return safe_normalize(transform_vector(xf, smooth), ph.gn);   // intersection.h:994-1013
 }
 
 // Trace + QueryBVH, render.cpp:17-62 + intersection.h:751-799: near-first DFS over the scene
 // BVH with NO closest-t culling; the callback keeps `t < minT && t > 0` (first found wins ties).
-TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNormal)
+// This is the reference's visit order, bit for bit.
+TB_ORDERED_ATTR Hit trace_ordered(const DScene& sc, V3 o, V3 d, float time, bool wantNormal)
 {
     V3 rcp;
     rcp.x = 1.0f / d.x;
@@ -295,19 +314,19 @@ TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNorm
 
     float minT = FLT_MAX;
     int closest = -1;
-    V3 closestN = v3s(0.0f);
+    PrimHit best;
+    best.t = 0.0f; best.tri = 0; best.u = best.v = best.w = 0.0f; best.gn = v3s(0.0f);
 
     while (count) {
         const uint32_t ref = stack[--count];
         if (ref & TB_LEAF) {
             const int index = (int)(ref & ~TB_LEAF);
-            float t;
-            V3 n = v3s(0.0f);
-            if (prim_intersect(sc, sc.prims[index], o, d, time, wantNormal, t, n)) {
-                if (t < minT && t > 0.0f) {
-                    minT = t;
+            PrimHit ph;
+            if (prim_test(sc, sc.prims[index], o, d, time, ph)) {
+                if (ph.t < minT && ph.t > 0.0f) {
+                    minT = ph.t;
                     closest = index;
-                    closestN = n;
+                    best = ph;
                 }
             }
         } else {
@@ -329,6 +348,80 @@ TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNorm
     Hit h;
     h.t = minT;
     h.prim = closest;
-    h.n = face_forward(closestN, -d);
+    V3 n = v3s(0.0f);
+    if (wantNormal && closest >= 0) n = prim_normal(sc, sc.prims[closest], o, d, time, best);
+    h.n = face_forward(n, -d);
+    return h;
+}
+
+// Flat scene program.  For small scenes (<= 16 primitives) the ordered walk above spends most of
+// its instructions on boxes that cannot miss: planes have +-1e8 bounds (intersection.h:919-924),
+// so every subtree holding one is "hit" for any ray that starts inside |o| < 1e7.  Because the
+// scene level has no closest-t culling, the SET of primitives tested depends only on which nodes'
+// slab tests pass, never on the visit order; the order matters only when two primitives return
+// exactly the same t.  trace_closest() therefore walks the nodes in a fixed (warp-uniform) order,
+// evaluates the same slab test on every finite box, skips it on infinite ones, keeps min t, and
+// -- if it ever sees an exact tie, a NaN, or an origin outside the guard -- redoes the ray with
+// trace_ordered().  Same result bit for bit, ~1/3 of the instructions, no stack, no type-switch
+// divergence (all lanes test the same primitive at the same time).
+struct __align__(16) FlatNode {
+    float lo[3];
+    float hi[3];
+    int parent;      // index of the parent node in this array (always smaller)
+    int info;        // bit0 leaf, bit1 infinite box, bits 8.. primitive index
+};
+
+TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNormal)
+{
+    const int n = sc.numFlat;
+    const bool guard = (fabsf(o.x) < 1.0e7f) & (fabsf(o.y) < 1.0e7f) & (fabsf(o.z) < 1.0e7f) & (d.x == d.x) & (d.y == d.y) &
+                       (d.z == d.z);
+    if (n == 0 || !guard) return trace_ordered(sc, o, d, time, wantNormal);
+
+    V3 rcp;
+    rcp.x = 1.0f / d.x;
+    rcp.y = 1.0f / d.y;
+    rcp.z = 1.0f / d.z;
+
+    float minT = FLT_MAX;
+    int closest = -1;
+    bool tie = false;
+    PrimHit best;
+    best.t = 0.0f; best.tri = 0; best.u = best.v = best.w = 0.0f; best.gn = v3s(0.0f);
+    uint32_t visited = 1u;   // node 0 is the root: no box test (intersection.h:759-763)
+
+    for (int i = 0; i < n; ++i) {
+        const FlatNode& nd = sc.flat[i];
+        const int info = nd.info;
+        bool v = i == 0 ? true : ((visited >> nd.parent) & 1u) != 0u;
+        if (v && i != 0 && !(info & 2)) {
+            float tbox;
+            v = ray_aabb(o, rcp, nd.lo[0], nd.lo[1], nd.lo[2], nd.hi[0], nd.hi[1], nd.hi[2], tbox);
+        }
+        if (!v) continue;
+        visited |= 1u << i;
+        if (info & 1) {
+            const int index = info >> 8;
+            PrimHit ph;
+            if (prim_test(sc, sc.prims[index], o, d, time, ph)) {
+                if (ph.t > 0.0f) {
+                    if (ph.t < minT) {
+                        minT = ph.t;
+                        closest = index;
+                        best = ph;
+                    } else if (ph.t == minT) {
+                        tie = true;
+                    }
+                }
+            }
+        }
+    }
+    if (tie) return trace_ordered(sc, o, d, time, wantNormal);
+    Hit h;
+    h.t = minT;
+    h.prim = closest;
+    V3 nrm = v3s(0.0f);
+    if (wantNormal && closest >= 0) nrm = prim_normal(sc, sc.prims[closest], o, d, time, best);
+    h.n = face_forward(nrm, -d);
     return h;
 }

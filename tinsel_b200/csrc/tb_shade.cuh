@@ -391,8 +391,12 @@ TB_DEV void path_hit(const DScene& sc, PathState& ps, const Hit& h, int bounce, 
         sf.etaO = 1.0f;
         sf.outAbsorb = v3s(0.0f);
     }
-    const V3 e = -ps.absorb * h.t;
-    ps.T = ps.T * v3(tbm_expf(e.x), tbm_expf(e.y), tbm_expf(e.z));
+    // pathThroughput *= Exp(-rayAbsorption*t), render.cpp:272.  With zero absorption the argument is
+    // -0*t = -0 and expf(-0) = 1 exactly, so the multiply is the identity and is skipped.
+    if (!(ps.absorb.x == 0.0f && ps.absorb.y == 0.0f && ps.absorb.z == 0.0f)) {
+        const V3 e = -ps.absorb * h.t;
+        ps.T = ps.T * v3(tbm_expf(e.x), tbm_expf(e.y), tbm_expf(e.z));
+    }
 
     sf.prim = h.prim;
     sf.p = ps.o + ps.d * h.t;

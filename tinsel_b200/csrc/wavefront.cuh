@@ -54,6 +54,7 @@ struct WfShared {
     // scene tables staged on chip
     DPrim prims[TB_WF_MAX_PRIMS];
     BvhPair pairs[TB_WF_MAX_PAIRS];
+    FlatNode flat[32];
 };
 
 
@@ -149,6 +150,13 @@ __global__ void __launch_bounds__(TB_WF_THREADS, 1) k_wavefront(LaunchParams P, 
             for (int i = tid; i < words; i += TB_WF_THREADS) dst[i] = src[i];
             sc.pairs = S.pairs;
         }
+    }
+    if (sc.numFlat > 0 && sc.numFlat <= 32) {
+        const int words = sc.numFlat * (int)(sizeof(FlatNode) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.flat);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(S.flat);
+        for (int i = tid; i < words; i += TB_WF_THREADS) dst[i] = src[i];
+        sc.flat = S.flat;
     }
     for (int s = tid; s < TB_WF_PATHS; s += TB_WF_THREADS) S.flags[s] = 0u;
     if (tid == 0) {
