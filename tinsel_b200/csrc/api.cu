@@ -261,7 +261,7 @@ struct tb200_renderer {
     size_t registeredBytes = 0;
     void* lastOutput = nullptr;
 
-    int pipeline = 1;             // 0 = mega (validation), 1 = wavefront
+    int pipeline = 2;             // 0 = mega (validation), 1 = wavefront v1, 2 = wavefront (product)
     tb200_stats stats;
 };
 
@@ -467,8 +467,10 @@ bool launch_frames(tb200_renderer* r, LaunchParams& P)
             P.numFrames = std::min(framesPerLaunch, frames - f);
             if (r->pipeline == 0)
                 launch_mega(P, r->stream, &launches);
-            else
+            else if (r->pipeline == 1)
                 launch_wavefront(P, r->numSMs, r->stream, &launches);
+            else
+                launch_wavefront2(P, r->numSMs, r->stream, &launches);
         }
         P.frame0 = frame0;
         P.numFrames = frames;
@@ -563,6 +565,7 @@ tb200_renderer* tb200_create(const tb200_scene* scene, int device)
     }
     const char* pipe = getenv("TINSEL_B200_PIPELINE");
     if (pipe && strcmp(pipe, "mega") == 0) r->pipeline = 0;
+    if (pipe && strcmp(pipe, "wavefront1") == 0) r->pipeline = 1;
     if (cudaMalloc((void**)&r->dCounter, sizeof(unsigned long long)) != cudaSuccess) {
         set_error("tb200_create: counter allocation failed");
         tb200_destroy(r);

@@ -149,3 +149,4 @@ void launch_normals(const LaunchParams& p, cudaStream_t stream, unsigned long lo
 // Wavefront pipeline: see wavefront.cuh
 // ------------------------------------------------------------------------------------------------
 #include "wavefront.cuh"
+#include "wavefront2.cuh"

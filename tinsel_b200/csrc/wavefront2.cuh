@@ -1,0 +1,458 @@
+// wavefront2.cuh -- the product pipeline: a persistent, CTA-resident wavefront path tracer with a
+// dedicated traversal stage.
+//
+// One CTA per SM stays resident for the whole launch and owns TB_WF2_PATHS path slots whose ENTIRE
+// inter-stage state lives in SHARED MEMORY (SoA, 45 words per path: path state, pending shadow ray,
+// hit records, next-event-estimation cursor).  A global-memory wavefront (tinsel's own unfinished
+// wavefront.cu keeps ~150 B/path in DRAM and re-reads it in five kernels per bounce,
+// wavefront.cu:765-796,1357-1375) would make queue traffic, not the scene, the HBM consumer; here
+// HBM only sees scene misses and the framebuffer reductions.
+//
+// Every slot that is alive has exactly one pending ray: its extension ray or one shadow ray.  The
+// CTA loops over three stages, each running over a queue compacted with warp ballot + prefix sum
+// (one shared atomic per warp), separated by __syncthreads():
+//
+//   T  trace    all pending rays (queue qT): closest hit -> hit record; classifies the slot into
+//               qA (extension rays) or qB (shadow rays).  Pure traversal: small register footprint,
+//               every lane does the same thing.
+//   S  shade    qA: miss -> sky, finish; hit -> absorption, emission MIS, first NEE sample.
+//               qB: connect the traced NEE sample; next NEE sample, or BSDF sample + throughput
+//               update + next extension ray.  Surviving slots go to the next qT, finished to qF.
+//   R  finish + regenerate (qF): splat the finished sample into the accumulator, claim a new
+//               sample index from the global counter, generate its camera ray -> next qT.
+//
+// Regeneration keeps the slots full until the counter runs dry; compaction keeps every stage on
+// full warps regardless of bounce depth or path termination.
+#pragma once
+
+#ifndef TB_WF2_THREADS
+#define TB_WF2_THREADS 512
+#endif
+#ifndef TB_WF2_PATHS
+#define TB_WF2_PATHS 1024
+#endif
+#define TB_WF2_MAX_PRIMS 48
+#define TB_WF2_MAX_PAIRS 48
+
+enum { WF2_PH_EXT = 0, WF2_PH_NEE = 1 };
+
+struct Wf2Shared {
+    // path state
+    float ox[TB_WF2_PATHS], oy[TB_WF2_PATHS], oz[TB_WF2_PATHS];
+    float dx[TB_WF2_PATHS], dy[TB_WF2_PATHS], dz[TB_WF2_PATHS];
+    float time[TB_WF2_PATHS];
+    float Tx[TB_WF2_PATHS], Ty[TB_WF2_PATHS], Tz[TB_WF2_PATHS];
+    float Lx[TB_WF2_PATHS], Ly[TB_WF2_PATHS], Lz[TB_WF2_PATHS];
+    float eta[TB_WF2_PATHS];
+    float ax[TB_WF2_PATHS], ay[TB_WF2_PATHS], az[TB_WF2_PATHS];
+    float bsdfPdf[TB_WF2_PATHS];
+    uint32_t rng1[TB_WF2_PATHS], rng2[TB_WF2_PATHS];
+    uint32_t sample[TB_WF2_PATHS];    // sample index within the launch
+    uint32_t flags[TB_WF2_PATHS];     // bits 1-2 rayType, bit 3 phase, bits 8.. bounce
+    // extension-ray hit
+    float ht[TB_WF2_PATHS], hnx[TB_WF2_PATHS], hny[TB_WF2_PATHS], hnz[TB_WF2_PATHS];
+    int hprim[TB_WF2_PATHS];
+    // pending shadow ray (origin is recomputed from the surface point) and its result
+    float sdx[TB_WF2_PATHS], sdy[TB_WF2_PATHS], sdz[TB_WF2_PATHS];
+    float sdist[TB_WF2_PATHS];
+    float slx[TB_WF2_PATHS], sly[TB_WF2_PATHS], slz[TB_WF2_PATHS];
+    float spdf[TB_WF2_PATHS];
+    int slight[TB_WF2_PATHS];
+    float st[TB_WF2_PATHS];
+    int sprim[TB_WF2_PATHS];
+    // NEE cursor
+    float sumx[TB_WF2_PATHS], sumy[TB_WF2_PATHS], sumz[TB_WF2_PATHS];
+    float lax[TB_WF2_PATHS], lay[TB_WF2_PATHS], laz[TB_WF2_PATHS];
+    uint32_t cursor[TB_WF2_PATHS];    // slot | prim << 8 | sample << 20
+    // queues
+    uint16_t qT[2][TB_WF2_PATHS];
+    uint16_t qA[TB_WF2_PATHS], qB[TB_WF2_PATHS], qF[TB_WF2_PATHS];
+    int nT[2], nA, nB, nF;
+    int exhausted;
+    // scene tables staged on chip
+    DPrim prims[TB_WF2_MAX_PRIMS];
+    BvhPair pairs[TB_WF2_MAX_PAIRS];
+    FlatNode flat[32];
+};
+
+// append `slot` to a shared queue for every lane with flag == true: ballot + prefix sum
+TB_DEV void wf2_push(uint16_t* queue, int* count, bool flag, int slot)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (flag) queue[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)slot;
+}
+
+TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s)
+{
+    // the quantities path_hit() derives from the path and the hit record (render.cpp:255-278)
+    Surface sf;
+    const V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
+    const V3 d = v3(S.dx[s], S.dy[s], S.dz[s]);
+    sf.prim = S.hprim[s];
+    sf.p = o + d * S.ht[s];
+    sf.n = v3(S.hnx[s], S.hny[s], S.hnz[s]);
+    sf.wo = -d;
+    sf.etaI = S.eta[s];
+    const DPrim& prim = sc.prims[sf.prim];
+    if (sf.etaI == 1.0f) {
+        sf.etaO = prim.mat.ior;
+        sf.outAbsorb = prim.mat.absorption;
+    } else {
+        sf.etaO = 1.0f;
+        sf.outAbsorb = v3s(0.0f);
+    }
+    return sf;
+}
+
+TB_DEV void wf2_store_shadow(Wf2Shared& S, int s, const ShadowRay& sr, const NeeCursor& c)
+{
+    S.sdx[s] = sr.d.x; S.sdy[s] = sr.d.y; S.sdz[s] = sr.d.z;
+    S.sdist[s] = sr.dist;
+    S.slx[s] = sr.lightN.x; S.sly[s] = sr.lightN.y; S.slz[s] = sr.lightN.z;
+    S.spdf[s] = sr.skyPdf;
+    S.slight[s] = sr.light;
+    S.sumx[s] = c.sum.x; S.sumy[s] = c.sum.y; S.sumz[s] = c.sum.z;
+    S.lax[s] = c.Lacc.x; S.lay[s] = c.Lacc.y; S.laz[s] = c.Lacc.z;
+    S.cursor[s] = (uint32_t)c.slot | ((uint32_t)c.prim << 8) | ((uint32_t)c.sample << 20);
+}
+
+// finish the shading of a surface hit once all NEE samples are folded: BSDF sample, next ray
+// (path_scatter) or termination.  Returns true when the slot continues with a new extension ray.
+TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf, V3 T, V3 L, Rng rng, float time, V3 neeSum,
+                        int bounce, int maxDepth)
+{
+    PathState ps;
+    ps.o = v3s(0.0f);
+    ps.d = v3s(0.0f);
+    ps.time = time;
+    ps.T = T;
+    ps.L = L;
+    ps.eta = sf.etaI;
+    ps.absorb = v3(S.ax[s], S.ay[s], S.az[s]);
+    ps.rayType = (int)((S.flags[s] >> 1) & 3u);
+    ps.bsdfPdf = S.bsdfPdf[s];
+    ps.rng = rng;
+    bool go;
+    if (bounce + 1 >= maxDepth) {
+        // the scattered ray of the final bounce is never traced (render.cpp:250): fold NEE only
+        ps.L = ps.L + ps.T * neeSum;
+        go = false;
+    } else {
+        go = path_scatter(sc, ps, sf, neeSum);
+    }
+    S.Lx[s] = ps.L.x; S.Ly[s] = ps.L.y; S.Lz[s] = ps.L.z;
+    if (!go) return false;
+    S.ox[s] = ps.o.x; S.oy[s] = ps.o.y; S.oz[s] = ps.o.z;
+    S.dx[s] = ps.d.x; S.dy[s] = ps.d.y; S.dz[s] = ps.d.z;
+    S.Tx[s] = ps.T.x; S.Ty[s] = ps.T.y; S.Tz[s] = ps.T.z;
+    S.eta[s] = ps.eta;
+    S.ax[s] = ps.absorb.x; S.ay[s] = ps.absorb.y; S.az[s] = ps.absorb.z;
+    S.bsdfPdf[s] = ps.bsdfPdf;
+    S.rng1[s] = ps.rng.s1;
+    S.rng2[s] = ps.rng.s2;
+    S.flags[s] = ((uint32_t)ps.rayType << 1) | ((uint32_t)WF2_PH_EXT << 3) | ((uint32_t)(bounce + 1) << 8);
+    return true;
+}
+
+__global__ void __launch_bounds__(TB_WF2_THREADS, 1) k_wavefront2(LaunchParams P, unsigned long long total)
+{
+    extern __shared__ __align__(16) unsigned char wf_smem_raw[];
+    Wf2Shared& S = *reinterpret_cast<Wf2Shared*>(wf_smem_raw);
+    const int tid = threadIdx.x;
+
+    // ---- prologue: stage the scene tables on chip ---------------------------------------------
+    DScene sc = P.scene;
+    if (sc.numPrims <= TB_WF2_MAX_PRIMS) {
+        const int words = sc.numPrims * (int)(sizeof(DPrim) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.prims);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(S.prims);
+        for (int i = tid; i < words; i += TB_WF2_THREADS) dst[i] = src[i];
+        sc.prims = S.prims;
+    }
+    if (sc.numPairs <= TB_WF2_MAX_PAIRS) {
+        const int words = sc.numPairs * (int)(sizeof(BvhPair) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.pairs);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(S.pairs);
+        for (int i = tid; i < words; i += TB_WF2_THREADS) dst[i] = src[i];
+        sc.pairs = S.pairs;
+    }
+    if (sc.numFlat > 0 && sc.numFlat <= 32) {
+        const int words = sc.numFlat * (int)(sizeof(FlatNode) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.flat);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(S.flat);
+        for (int i = tid; i < words; i += TB_WF2_THREADS) dst[i] = src[i];
+        sc.flat = S.flat;
+    }
+    // every slot starts "finished with nothing to splat": stage R fills it with a camera sample
+    for (int s = tid; s < TB_WF2_PATHS; s += TB_WF2_THREADS) {
+        S.qF[s] = (uint16_t)s;
+        S.sample[s] = 0xffffffffu;
+    }
+    if (tid == 0) {
+        S.nT[0] = S.nT[1] = 0;
+        S.nA = S.nB = 0;
+        S.nF = TB_WF2_PATHS;
+        S.exhausted = 0;
+    }
+    __syncthreads();
+
+    const int maxDepth = P.film.maxDepth;
+    int cur = 0;   // qT[cur] is filled by stages S and R, consumed by stage T
+
+    for (;;) {
+        // ===================== stage R: splat finished samples, regenerate ========================
+        {
+            const int nF = S.nF;
+            for (int q0 = 0; q0 < nF; q0 += TB_WF2_THREADS) {
+                const int q = q0 + tid;
+                const bool active = q < nF;
+                const int s = active ? (int)S.qF[q] : 0;
+                if (active && S.sample[s] != 0xffffffffu) {
+                    int px, py, frame;
+                    decode_sample(P, (unsigned long long)S.sample[s], px, py, frame);
+                    // raster position of the sample: its first two RNG draws (render.cpp:476,481-482)
+                    Rng rr = rng_seed(tb_sample_seed((uint32_t)(py * P.film.width + px), (uint32_t)frame));
+                    float rx = rng_float(rr);
+                    float ry = rng_float(rr);
+                    rx += px;
+                    ry += py;
+                    sample_end(P, px, py, rx, ry, v3(S.Lx[s], S.Ly[s], S.Lz[s]));
+                    S.sample[s] = 0xffffffffu;
+                }
+                // claim a new sample; indices on tile padding outside the image are skipped
+                bool want = active && !*(volatile int*)&S.exhausted;
+                bool fresh = false;
+                for (int attempt = 0; attempt < 64; ++attempt) {
+                    if (!__any_sync(0xffffffffu, want)) break;
+                    const unsigned m = __ballot_sync(0xffffffffu, want);
+                    const int lane = tid & 31;
+                    const int leader = __ffs(m) - 1;
+                    unsigned long long base = 0ull;
+                    if (lane == leader) {
+                        base = atomicAdd(P.sampleCounter, (unsigned long long)__popc(m));
+                        if (base + __popc(m) >= total) *(volatile int*)&S.exhausted = 1;
+                    }
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    const unsigned long long idx = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+                    if (want) {
+                        if (idx >= total) {
+                            want = false;
+                        } else {
+                            int px, py, frame;
+                            if (decode_sample(P, idx, px, py, frame)) {
+                                PathState ps;
+                                float rx, ry;
+                                sample_begin(P, px, py, frame, ps, rx, ry);
+                                S.ox[s] = ps.o.x; S.oy[s] = ps.o.y; S.oz[s] = ps.o.z;
+                                S.dx[s] = ps.d.x; S.dy[s] = ps.d.y; S.dz[s] = ps.d.z;
+                                S.time[s] = ps.time;
+                                S.Tx[s] = 1.0f; S.Ty[s] = 1.0f; S.Tz[s] = 1.0f;
+                                S.Lx[s] = 0.0f; S.Ly[s] = 0.0f; S.Lz[s] = 0.0f;
+                                S.eta[s] = 1.0f;
+                                S.ax[s] = 0.0f; S.ay[s] = 0.0f; S.az[s] = 0.0f;
+                                S.bsdfPdf[s] = 1.0f;
+                                S.rng1[s] = ps.rng.s1;
+                                S.rng2[s] = ps.rng.s2;
+                                S.sample[s] = (uint32_t)idx;
+                                S.flags[s] = ((uint32_t)TB_REFLECTED << 1) | ((uint32_t)WF2_PH_EXT << 3);
+                                fresh = true;
+                                want = false;
+                            }
+                        }
+                    }
+                }
+                wf2_push(S.qT[cur], &S.nT[cur], fresh, s);
+            }
+        }
+        __syncthreads();
+        const int nT = S.nT[cur];
+        if (nT == 0) break;   // nothing alive and nothing left to regenerate
+        if (tid == 0) {
+            S.nF = 0;
+            S.nT[cur ^ 1] = 0;
+        }
+
+        // ===================== stage T: trace every pending ray ===================================
+        for (int q0 = 0; q0 < nT; q0 += TB_WF2_THREADS) {
+            const int q = q0 + tid;
+            const bool active = q < nT;
+            const int s = active ? (int)S.qT[cur][q] : 0;
+            bool isExt = false, isNee = false;
+            if (active) {
+                const uint32_t fl = S.flags[s];
+                const V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
+                const V3 d = v3(S.dx[s], S.dy[s], S.dz[s]);
+                const float time = S.time[s];
+                if (((fl >> 3) & 1u) == WF2_PH_EXT) {
+                    if (maxDepth > 0) {
+                        const Hit h = trace_closest(sc, o, d, time, true);
+                        S.ht[s] = h.t;
+                        S.hnx[s] = h.n.x; S.hny[s] = h.n.y; S.hnz[s] = h.n.z;
+                        S.hprim[s] = h.prim;
+                    } else {
+                        S.hprim[s] = -2;   // maxDepth == 0: no trace at all, radiance stays 0
+                    }
+                    isExt = true;
+                } else {
+                    // shadow ray from the surface point: origin = p + FaceForward(n, wi)*eps (render.cpp:121,170)
+                    const V3 p = o + d * S.ht[s];
+                    const V3 n = v3(S.hnx[s], S.hny[s], S.hnz[s]);
+                    const V3 wi = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
+                    const Hit h = trace_closest(sc, p + face_forward(n, wi) * TB_RAY_EPS, wi, time, false);
+                    S.st[s] = h.t;
+                    S.sprim[s] = h.prim;
+                    isNee = true;
+                }
+            }
+            wf2_push(S.qA, &S.nA, isExt, s);
+            wf2_push(S.qB, &S.nB, isNee, s);
+        }
+        __syncthreads();
+        const int nA = S.nA, nB = S.nB;
+        cur ^= 1;   // stages S and R fill the other qT
+        __syncthreads();
+        if (tid == 0) {
+            S.nA = 0;
+            S.nB = 0;
+        }
+
+        // ===================== stage S/A: extension-ray results ===================================
+        for (int q0 = 0; q0 < nA; q0 += TB_WF2_THREADS) {
+            const int q = q0 + tid;
+            const bool active = q < nA;
+            const int s = active ? (int)S.qA[q] : 0;
+            bool cont = false, fin = false;
+            if (active) {
+                const uint32_t fl = S.flags[s];
+                const int bounce = (int)(fl >> 8);
+                const int hprim = S.hprim[s];
+                if (hprim < 0) {
+                    if (hprim == -1) {
+                        PathState ps;
+                        ps.d = v3(S.dx[s], S.dy[s], S.dz[s]);
+                        ps.T = v3(S.Tx[s], S.Ty[s], S.Tz[s]);
+                        ps.L = v3(S.Lx[s], S.Ly[s], S.Lz[s]);
+                        ps.rayType = (int)((fl >> 1) & 3u);
+                        ps.bsdfPdf = S.bsdfPdf[s];
+                        path_miss(sc, ps, bounce);
+                        S.Lx[s] = ps.L.x; S.Ly[s] = ps.L.y; S.Lz[s] = ps.L.z;
+                    }
+                    fin = true;
+                } else {
+                    // hit prologue (render.cpp:255-310)
+                    PathState ps;
+                    ps.o = v3(S.ox[s], S.oy[s], S.oz[s]);
+                    ps.d = v3(S.dx[s], S.dy[s], S.dz[s]);
+                    ps.time = S.time[s];
+                    ps.T = v3(S.Tx[s], S.Ty[s], S.Tz[s]);
+                    ps.L = v3(S.Lx[s], S.Ly[s], S.Lz[s]);
+                    ps.eta = S.eta[s];
+                    ps.absorb = v3(S.ax[s], S.ay[s], S.az[s]);
+                    ps.rayType = (int)((fl >> 1) & 3u);
+                    ps.bsdfPdf = S.bsdfPdf[s];
+                    ps.rng.s1 = S.rng1[s];
+                    ps.rng.s2 = S.rng2[s];
+                    Hit h;
+                    h.t = S.ht[s];
+                    h.n = v3(S.hnx[s], S.hny[s], S.hnz[s]);
+                    h.prim = hprim;
+                    Surface sf;
+                    path_hit(sc, ps, h, bounce, sf);
+                    NeeCursor c;
+                    nee_begin(c);
+                    ShadowRay sr;
+                    if (nee_generate(sc, sf, ps.time, c, ps.rng, sr)) {
+                        S.Tx[s] = ps.T.x; S.Ty[s] = ps.T.y; S.Tz[s] = ps.T.z;
+                        S.Lx[s] = ps.L.x; S.Ly[s] = ps.L.y; S.Lz[s] = ps.L.z;
+                        S.rng1[s] = ps.rng.s1;
+                        S.rng2[s] = ps.rng.s2;
+                        wf2_store_shadow(S, s, sr, c);
+                        S.flags[s] = (fl & ~(1u << 3)) | ((uint32_t)WF2_PH_NEE << 3);
+                        cont = true;
+                    } else {
+                        // scene without lights or probe: straight to the BSDF
+                        cont = wf2_scatter(S, sc, s, sf, ps.T, ps.L, ps.rng, ps.time, c.sum, bounce, maxDepth);
+                        fin = !cont;
+                    }
+                }
+            }
+            wf2_push(S.qT[cur], &S.nT[cur], cont, s);
+            wf2_push(S.qF, &S.nF, fin, s);
+        }
+
+        // ===================== stage S/B: shadow-ray results =======================================
+        for (int q0 = 0; q0 < nB; q0 += TB_WF2_THREADS) {
+            const int q = q0 + tid;
+            const bool active = q < nB;
+            const int s = active ? (int)S.qB[q] : 0;
+            bool cont = false, fin = false;
+            if (active) {
+                const uint32_t fl = S.flags[s];
+                const int bounce = (int)(fl >> 8);
+                const Surface sf = wf2_surface(S, sc, s);
+                ShadowRay sr;
+                sr.o = v3s(0.0f);
+                sr.d = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
+                sr.dist = S.sdist[s];
+                sr.lightN = v3(S.slx[s], S.sly[s], S.slz[s]);
+                sr.skyPdf = S.spdf[s];
+                sr.light = S.slight[s];
+                NeeCursor c;
+                const uint32_t cw = S.cursor[s];
+                c.slot = (int)(cw & 0xffu);
+                c.prim = (int)((cw >> 8) & 0xfffu);
+                c.sample = (int)(cw >> 20);
+                c.sum = v3(S.sumx[s], S.sumy[s], S.sumz[s]);
+                c.Lacc = v3(S.lax[s], S.lay[s], S.laz[s]);
+                Hit sh;
+                sh.t = S.st[s];
+                sh.prim = S.sprim[s];
+                sh.n = v3s(0.0f);
+                nee_connect(sc, sf, sr, sh, c);
+
+                Rng rng;
+                rng.s1 = S.rng1[s];
+                rng.s2 = S.rng2[s];
+                const float time = S.time[s];
+                if (nee_generate(sc, sf, time, c, rng, sr)) {
+                    S.rng1[s] = rng.s1;
+                    S.rng2[s] = rng.s2;
+                    wf2_store_shadow(S, s, sr, c);
+                    cont = true;
+                } else {
+                    cont = wf2_scatter(S, sc, s, sf, v3(S.Tx[s], S.Ty[s], S.Tz[s]), v3(S.Lx[s], S.Ly[s], S.Lz[s]), rng, time, c.sum,
+                                       bounce, maxDepth);
+                    fin = !cont;
+                }
+            }
+            wf2_push(S.qT[cur], &S.nT[cur], cont, s);
+            wf2_push(S.qF, &S.nF, fin, s);
+        }
+        __syncthreads();
+    }
+}
+
+void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
+{
+    const unsigned long long total = p.samplesPerFrame * (unsigned long long)p.numFrames;
+    if (total == 0ull) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_wavefront2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wf2Shared));
+        configured = true;
+    }
+    cudaMemsetAsync(p.sampleCounter, 0, sizeof(unsigned long long), stream);
+    // one resident CTA per SM; small jobs use fewer CTAs so that every CTA has a full slot array
+    unsigned long long want = (total + TB_WF2_PATHS - 1) / TB_WF2_PATHS;
+    int grid = numSMs > 0 ? numSMs : 148;
+    if (want < (unsigned long long)grid) grid = (int)want;
+    if (grid < 1) grid = 1;
+    k_wavefront2<<<grid, TB_WF2_THREADS, sizeof(Wf2Shared), stream>>>(p, total);
+    if (launchCount) ++*launchCount;
+}
