@@ -133,36 +133,55 @@ uint32_t build_pairs(const tb200_bvh_node* nodes, int numNodes, std::vector<BvhP
     return ref_of(0);
 }
 
-// Flat scene program for trace_closest() (tb_scene.cuh): the scene BVH's nodes in an order where
-// parents precede children.  Built only for scenes of at most 16 primitives (<= 31 nodes, one
-// bit each in the per-ray visited mask).
-void build_flat(const tb200_bvh_node* nodes, int numNodes, int numPrims, std::vector<FlatNode>* out)
+// Flat scene program for trace_closest() (tb_scene.cuh).  Walks the scene BVH once; infinite
+// boxes (planes' +-1e8 bounds and every ancestor of one) are transparent, finite interior boxes get
+// a bit in the per-ray mask, leaves become LEAF / LEAFBOX / PLANE ops guarded by the bit of their
+// nearest finite ancestor.  Built only for scenes of at most 16 primitives.
+void build_program(const tb200_scene* sc, std::vector<ProgOp>* out)
 {
     out->clear();
-    if (numNodes <= 0 || numNodes > 31 || numPrims > 16) return;
-    struct Item { uint32_t node; int parent; };
+    const tb200_bvh_node* nodes = sc->bvhNodes;
+    if (sc->numBvhNodes <= 0 || sc->numPrimitives > 16) return;
+    struct Item { uint32_t node; int guard; bool isRoot; };
     std::vector<Item> todo;
-    todo.push_back({0u, -1});
+    todo.push_back({0u, TB_BIT_ALWAYS, true});
+    int nextBit = 0;
     while (!todo.empty()) {
         const Item it = todo.back();
         todo.pop_back();
         const tb200_bvh_node& n = nodes[it.node];
-        FlatNode f;
-        memcpy(f.lo, n.lower, 12);
-        memcpy(f.hi, n.upper, 12);
-        f.parent = it.parent < 0 ? 0 : it.parent;
         const bool leaf = (n.right_leaf >> 31) != 0;
         bool infinite = true;
         for (int k = 0; k < 3; ++k) infinite = infinite && n.lower[k] <= -5.0e7f && n.upper[k] >= 5.0e7f;
-        f.info = (leaf ? 1 : 0) | (infinite ? 2 : 0) | (leaf ? int(n.left) << 8 : 0);
-        const int me = int(out->size());
-        out->push_back(f);
-        if (!leaf) {
-            todo.push_back({n.right_leaf & 0x7fffffffu, me});
-            todo.push_back({n.left, me});
+        if (it.isRoot) infinite = true;   // the root's own box is never tested (intersection.h:759-763)
+        ProgOp op;
+        memset(&op, 0, sizeof(op));
+        op.a[0] = n.lower[0]; op.a[1] = n.lower[1]; op.a[2] = n.lower[2]; op.a[3] = n.upper[0];
+        op.b[0] = n.upper[1]; op.b[1] = n.upper[2];
+        if (leaf) {
+            const tb200_primitive& p = sc->primitives[n.left];
+            int kind = infinite ? TB_OP_LEAF : TB_OP_LEAFBOX;
+            if (infinite && p.type == TB200_PLANE) {
+                kind = TB_OP_PLANE;
+                memcpy(op.a, p.plane, 16);
+            }
+            op.kindPrim = kind | (int(n.left) << 8);
+            op.bits = it.guard;
+            out->push_back(op);
+        } else {
+            int guard = it.guard;
+            if (!infinite) {
+                if (nextBit >= 31) { out->clear(); return; }
+                op.kindPrim = TB_OP_BOX;
+                op.bits = it.guard | (nextBit << 8);
+                out->push_back(op);
+                guard = nextBit++;
+            }
+            todo.push_back({n.right_leaf & 0x7fffffffu, guard, false});
+            todo.push_back({n.left, guard, false});
         }
     }
-    if (out->size() > 31) out->clear();
+    if (out->size() > 32) out->clear();
 }
 
 // CameraSampler constructor, util.h:49-71, with Mat44(Transform) (maths.h:841-849), Mat33(Quat)
@@ -244,7 +263,7 @@ struct tb200_renderer {
     DScene scene;
     DPrim* dPrims = nullptr;
     BvhPair* dScenePairs = nullptr;
-    FlatNode* dFlat = nullptr;
+    ProgOp* dFlat = nullptr;
     DMesh* dMeshes = nullptr;
     std::vector<void*> owned;   // every other device allocation
 
@@ -261,7 +280,7 @@ struct tb200_renderer {
     size_t registeredBytes = 0;
     void* lastOutput = nullptr;
 
-    int pipeline = 2;             // 0 = mega (validation), 1 = wavefront v1, 2 = wavefront (product)
+    int pipeline = 2;             // 0 = mega (validation), 2 = wavefront (product)
     tb200_stats stats;
 };
 
@@ -379,8 +398,8 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
     sc.numPrims = s->numPrimitives;
     sc.pairs = r->dScenePairs;
     sc.numPairs = (int)scenePairs.size();
-    std::vector<FlatNode> flat;
-    if (!getenv("TINSEL_B200_NO_FLAT")) build_flat(s->bvhNodes, s->numBvhNodes, s->numPrimitives, &flat);
+    std::vector<ProgOp> flat;
+    if (!getenv("TINSEL_B200_NO_FLAT")) build_program(s, &flat);
     if (!upload(flat, &r->dFlat, h2d)) return false;
     sc.flat = r->dFlat;
     sc.numFlat = (int)flat.size();
@@ -467,8 +486,6 @@ bool launch_frames(tb200_renderer* r, LaunchParams& P)
             P.numFrames = std::min(framesPerLaunch, frames - f);
             if (r->pipeline == 0)
                 launch_mega(P, r->stream, &launches);
-            else if (r->pipeline == 1)
-                launch_wavefront(P, r->numSMs, r->stream, &launches);
             else
                 launch_wavefront2(P, r->numSMs, r->stream, &launches);
         }
@@ -565,7 +582,6 @@ tb200_renderer* tb200_create(const tb200_scene* scene, int device)
     }
     const char* pipe = getenv("TINSEL_B200_PIPELINE");
     if (pipe && strcmp(pipe, "mega") == 0) r->pipeline = 0;
-    if (pipe && strcmp(pipe, "wavefront1") == 0) r->pipeline = 1;
     if (cudaMalloc((void**)&r->dCounter, sizeof(unsigned long long)) != cudaSuccess) {
         set_error("tb200_create: counter allocation failed");
         tb200_destroy(r);

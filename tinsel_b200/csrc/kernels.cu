@@ -146,7 +146,6 @@ void launch_normals(const LaunchParams& p, cudaStream_t stream, unsigned long lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// Wavefront pipeline: see wavefront.cuh
+// Wavefront pipeline: see wavefront2.cuh
 // ------------------------------------------------------------------------------------------------
-#include "wavefront.cuh"
 #include "wavefront2.cuh"

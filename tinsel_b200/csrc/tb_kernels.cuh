@@ -29,7 +29,5 @@ void finalize_params(LaunchParams* p);
 void launch_mega(const LaunchParams& p, cudaStream_t stream, unsigned long long* launchCount);
 // persistent CTA-resident wavefront pipeline with a dedicated traversal stage (the product path)
 void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount);
-// first-generation wavefront (two fused stages); kept for A/B timing while the new one settles
-void launch_wavefront(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount);
 // eNormals mode (render.cpp:494-515)
 void launch_normals(const LaunchParams& p, cudaStream_t stream, unsigned long long* launchCount);

@@ -93,7 +93,7 @@ struct DScene {
     V3 horizon, zenith;
     DProbe probe;
     int numNee;               // shadow rays per surface hit: probe + sum(lightSamples)
-    const struct FlatNode* flat;   // flat scene program (nullptr / numFlat == 0: use the ordered walk)
+    const struct ProgOp* flat;     // flat scene program (numFlat == 0: use the ordered walk)
     int numFlat;
 };
 
@@ -359,16 +359,23 @@ TB_ORDERED_ATTR Hit trace_ordered(const DScene& sc, V3 o, V3 d, float time, bool
 // so every subtree holding one is "hit" for any ray that starts inside |o| < 1e7.  Because the
 // scene level has no closest-t culling, the SET of primitives tested depends only on which nodes'
 // slab tests pass, never on the visit order; the order matters only when two primitives return
-// exactly the same t.  trace_closest() therefore walks the nodes in a fixed (warp-uniform) order,
-// evaluates the same slab test on every finite box, skips it on infinite ones, keeps min t, and
-// -- if it ever sees an exact tie, a NaN, or an origin outside the guard -- redoes the ray with
-// trace_ordered().  Same result bit for bit, ~1/3 of the instructions, no stack, no type-switch
-// divergence (all lanes test the same primitive at the same time).
-struct __align__(16) FlatNode {
-    float lo[3];
-    float hi[3];
-    int parent;      // index of the parent node in this array (always smaller)
-    int info;        // bit0 leaf, bit1 infinite box, bits 8.. primitive index
+// exactly the same t.  The host (api.cu: build_program) therefore compiles the scene BVH into a
+// short list of ops executed in a fixed, warp-uniform order:
+//   BOX      finite interior box: same slab test as the reference, result kept in a bit mask
+//   LEAFBOX  finite leaf box + primitive test          LEAF  primitive test behind infinite boxes
+//   PLANE    static plane with its coefficients inline (IntersectRayPlane ignores transforms)
+// each guarded by the bit of its nearest finite ancestor (infinite boxes are transparent).
+// trace_closest() keeps min t and -- if it ever sees an exact tie, a NaN direction, or an origin
+// outside the guard -- redoes the ray with trace_ordered().  Same result bit for bit, a fraction
+// of the instructions, no stack, no type-switch divergence.
+enum { TB_OP_BOX = 0, TB_OP_LEAFBOX = 1, TB_OP_LEAF = 2, TB_OP_PLANE = 3 };
+#define TB_BIT_ALWAYS 32
+
+struct __align__(16) ProgOp {
+    float a[4];      // BOX/LEAFBOX: lo.xyz, hi.x      PLANE: plane coefficients
+    float b[2];      // BOX/LEAFBOX: hi.y, hi.z
+    int kindPrim;    // kind | primitive index << 8
+    int bits;        // guard bit (TB_BIT_ALWAYS: unconditional) | own bit << 8 (BOX only)
 };
 
 TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNormal)
@@ -388,30 +395,48 @@ TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNorm
     bool tie = false;
     PrimHit best;
     best.t = 0.0f; best.tri = 0; best.u = best.v = best.w = 0.0f; best.gn = v3s(0.0f);
-    uint32_t visited = 1u;   // node 0 is the root: no box test (intersection.h:759-763)
+    uint32_t visited = 0u;
 
     for (int i = 0; i < n; ++i) {
-        const FlatNode& nd = sc.flat[i];
-        const int info = nd.info;
-        bool v = i == 0 ? true : ((visited >> nd.parent) & 1u) != 0u;
-        if (v && i != 0 && !(info & 2)) {
-            float tbox;
-            v = ray_aabb(o, rcp, nd.lo[0], nd.lo[1], nd.lo[2], nd.hi[0], nd.hi[1], nd.hi[2], tbox);
+        const float4 a = *reinterpret_cast<const float4*>(sc.flat[i].a);
+        const float4 bk = *reinterpret_cast<const float4*>(sc.flat[i].b);   // b[0], b[1], kindPrim, bits
+        const int kindPrim = __float_as_int(bk.z), bits = __float_as_int(bk.w);
+        const int gbit = bits & 0xff;
+        if (gbit != TB_BIT_ALWAYS && !((visited >> gbit) & 1u)) continue;
+        const int kind = kindPrim & 0xff;
+        if (kind == TB_OP_PLANE) {
+            // IntersectRayPlane, intersection.h:85-99
+            const float dd = a.x * d.x + a.y * d.y + a.z * d.z + a.w * 0.0f;
+            if (dd == 0.0f) continue;
+            const float t = -(a.x * o.x + a.y * o.y + a.z * o.z + a.w * 1.0f) / dd;
+            if (t > 0.0f) {
+                if (t < minT) {
+                    minT = t;
+                    closest = kindPrim >> 8;
+                } else if (t == minT) {
+                    tie = true;
+                }
+            }
+            continue;
         }
-        if (!v) continue;
-        visited |= 1u << i;
-        if (info & 1) {
-            const int index = info >> 8;
-            PrimHit ph;
-            if (prim_test(sc, sc.prims[index], o, d, time, ph)) {
-                if (ph.t > 0.0f) {
-                    if (ph.t < minT) {
-                        minT = ph.t;
-                        closest = index;
-                        best = ph;
-                    } else if (ph.t == minT) {
-                        tie = true;
-                    }
+        if (kind != TB_OP_LEAF) {
+            float tbox;
+            if (!ray_aabb(o, rcp, a.x, a.y, a.z, a.w, bk.x, bk.y, tbox)) continue;
+            if (kind == TB_OP_BOX) {
+                visited |= 1u << ((bits >> 8) & 0xff);
+                continue;
+            }
+        }
+        const int index = kindPrim >> 8;
+        PrimHit ph;
+        if (prim_test(sc, sc.prims[index], o, d, time, ph)) {
+            if (ph.t > 0.0f) {
+                if (ph.t < minT) {
+                    minT = ph.t;
+                    closest = index;
+                    best = ph;
+                } else if (ph.t == minT) {
+                    tie = true;
                 }
             }
         }

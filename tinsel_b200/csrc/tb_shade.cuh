@@ -135,26 +135,28 @@ TB_DEV V3 bsdf_eval(const DMaterial& mat, float etaI, float etaO, V3 N, V3 V, V3
             const float Fd90 = 0.5f + 2.0f * LDotH * LDotH * mat.roughness;
             const float Fd = tb_lerp(1.0f, Fd90, FL) * tb_lerp(1.0f, Fd90, FV);
 
-            const float Dr = gtr1_clearcoat(mat, NDotH);
-            const float Fc = tb_lerp(.04f, 1.0f, FH);
-            const float Gr = smith_ggx(NDotL, .25f) * smith_ggx(NDotV, .25f);
-
-            brdf = TB_INV_PI * Fd * mat.color * (1.0f - mat.metallic) * (1.0f - mat.subsurface) + Gs * Fs * Ds +
-                   v3s(mat.clearcoat * Gr * Fc * Dr);
+            brdf = TB_INV_PI * Fd * mat.color * (1.0f - mat.metallic) * (1.0f - mat.subsurface) + Gs * Fs * Ds;
+            // clearcoat lobe: `+ mat.clearcoat*Gr*Fc*Dr`.  With clearcoat == 0 the term is 0*finite = +-0
+            // (Gr, Fc, Dr are finite here: NDotL > 0, alpha in [.001,.1]) and adding it changes at most
+            // the sign of a zero, which no branch or sum downstream can observe; skip the lobe then.
+            if (mat.clearcoat != 0.0f) {
+                const float Dr = gtr1_clearcoat(mat, NDotH);
+                const float Fc = tb_lerp(.04f, 1.0f, FH);
+                const float Gr = smith_ggx(NDotL, .25f) * smith_ggx(NDotV, .25f);
+                brdf = brdf + v3s(mat.clearcoat * Gr * Fc * Dr);
+            }
         }
     }
     return tb_lerp(brdf, bsdf, mat.transmission);
 }
 
-// the GGX half-vector lobe shared by both branches of BSDFSample, disney.h:183-205 / 256-279
-TB_DEV V3 sample_ggx_reflection(const DMaterial& mat, float r1, float r2, V3 U, V3 Vt, V3 N, V3 view)
+// the GGX half-vector lobe shared by both branches of BSDFSample, disney.h:183-205 / 256-279;
+// sinPhiHalf / cosPhiHalf = sinf / cosf(r1*k2Pi) are computed by the caller
+TB_DEV V3 sample_ggx_reflection(const DMaterial& mat, float r2, float sinPhiHalf, float cosPhiHalf, V3 U, V3 Vt, V3 N, V3 view)
 {
     const float a = mat.alpha;
-    const float phiHalf = r1 * TB_2PI;
     const float cosThetaHalf = sqrtf((1.0f - r2) / (1.0f + (tb_sqr(a) - 1.0f) * r2));
     const float sinThetaHalf = sqrtf(tb_max(0.0f, 1.0f - tb_sqr(cosThetaHalf)));
-    float sinPhiHalf, cosPhiHalf;
-    tbm_sincosf(phiHalf, &sinPhiHalf, &cosPhiHalf);
     V3 half = U * (sinThetaHalf * cosPhiHalf) + Vt * (sinThetaHalf * sinPhiHalf) + N * cosThetaHalf;
     if (dot(half, view) <= 0.0f) half = half * -1.0f;
     return 2.0f * dot(view, half) * half - view;
@@ -162,16 +164,23 @@ TB_DEV V3 sample_ggx_reflection(const DMaterial& mat, float r1, float r2, V3 U, 
 
 // BSDFSample, disney.h:170-293.  Draw order: Randf(transmission?) -> [Randf(F?) -> Sample2D | -]
 // or Sample2D -> Randf(0.5) -> [Randf(subsurface?) -> (Randf,Randf) | -].
+// The three lobes that need sinf/cosf of an angle (GGX: r1*k2Pi, cosine: k2Pi*r2, uniform
+// hemisphere: k2Pi*Randf) first only pick their angle; one shared sincos call then serves all
+// lanes of the warp instead of three divergent ones (same values: the product is commutative).
 TB_DEV void bsdf_sample(const DMaterial& mat, float etaI, float etaO, V3 U, V3 Vt, V3 N, V3 view, V3& light, float& pdf,
                         int& type, Rng& rng)
 {
+    enum { LOBE_GGX, LOBE_COSINE, LOBE_UNIFORM };
+    int lobe;
+    float angleArg, r1 = 0.0f, r2 = 0.0f, uz = 0.0f;
     if (rng_float(rng) < mat.transmission) {
         const float F = fresnel_dielectric(dot(N, view), etaI, etaO);
         if (rng_float(rng) < F) {
-            const float r1 = rng_float(rng);
-            const float r2 = rng_float(rng);
+            r1 = rng_float(rng);
+            r2 = rng_float(rng);
             type = TB_REFLECTED;
-            light = sample_ggx_reflection(mat, r1, r2, U, Vt, N, view);
+            lobe = LOBE_GGX;
+            angleArg = r1;
         } else {
             const float eta = etaI / etaO;
             if (refract_dir(view, N, eta, light)) {
@@ -183,22 +192,40 @@ TB_DEV void bsdf_sample(const DMaterial& mat, float etaI, float etaO, V3 U, V3 V
             return;
         }
     } else {
-        const float r1 = rng_float(rng);
-        const float r2 = rng_float(rng);
+        r1 = rng_float(rng);
+        r2 = rng_float(rng);
         if (rng_float(rng) < 0.5f) {
             if (rng_float(rng) < mat.subsurface) {
-                const V3 d = uniform_sample_hemisphere(rng);
-                light = U * d.x + Vt * d.y - N * d.z;
+                // UniformSampleHemisphere(Random&), maths.h:1291-1302: z, then phi = k2Pi*Randf
+                uz = rng_float(rng);
+                angleArg = rng_float(rng);
+                lobe = LOBE_UNIFORM;
                 type = TB_TRANSMITTED;
             } else {
-                const V3 d = cosine_sample_hemisphere(r1, r2);
-                light = U * d.x + Vt * d.y + N * d.z;
+                lobe = LOBE_COSINE;
+                angleArg = r2;
                 type = TB_REFLECTED;
             }
         } else {
-            light = sample_ggx_reflection(mat, r1, r2, U, Vt, N, view);
+            lobe = LOBE_GGX;
+            angleArg = r1;
             type = TB_REFLECTED;
         }
+    }
+    float sn, cs;
+    tbm_sincosf(angleArg * TB_2PI, &sn, &cs);
+    if (lobe == LOBE_GGX) {
+        light = sample_ggx_reflection(mat, r2, sn, cs, U, Vt, N, view);
+    } else if (lobe == LOBE_COSINE) {
+        // CosineSampleHemisphere, maths.h:1319-1325 via UniformSampleDisc, maths.h:1304-1310
+        const float r = sqrtf(r1);
+        const float sx = r * cs, sy = r * sn;
+        const float z = sqrtf(tb_max(0.0f, 1.0f - sx * sx - sy * sy));
+        light = U * sx + Vt * sy + N * z;
+    } else {
+        const float w = sqrtf(1.0f - uz * uz);
+        const float dx = cs * w, dy = sn * w;
+        light = U * dx + Vt * dy - N * uz;
     }
     pdf = bsdf_pdf(mat, etaI, etaO, N, view, light);
 }

@@ -8,31 +8,36 @@
 // wavefront.cu:765-796,1357-1375) would make queue traffic, not the scene, the HBM consumer; here
 // HBM only sees scene misses and the framebuffer reductions.
 //
-// Every slot that is alive has exactly one pending ray: its extension ray or one shadow ray.  The
-// CTA loops over three stages, each running over a queue compacted with warp ballot + prefix sum
-// (one shared atomic per warp), separated by __syncthreads():
+// Every slot that is alive has exactly one pending ray: its extension ray or one shadow ray.  Each
+// CTA alternates between two phases separated by __syncthreads(), every stage running over a queue
+// compacted with warp ballot + prefix sum (one shared atomic per warp):
 //
-//   T  trace    all pending rays (queue qT): closest hit -> hit record; classifies the slot into
-//               qA (extension rays) or qB (shadow rays).  Pure traversal: small register footprint,
-//               every lane does the same thing.
-//   S  shade    qA: miss -> sky, finish; hit -> absorption, emission MIS, first NEE sample.
-//               qB: connect the traced NEE sample; next NEE sample, or BSDF sample + throughput
-//               update + next extension ray.  Surviving slots go to the next qT, finished to qF.
-//   R  finish + regenerate (qF): splat the finished sample into the accumulator, claim a new
-//               sample index from the global counter, generate its camera ray -> next qT.
+//   phase 1  R  finish + regenerate (queue qF): splat the finished sample into the accumulator,
+//               claim a new sample index from the global counter (one atomic per warp), generate
+//               its camera ray.
+//            T  trace every pending ray (queue qT): closest hit -> hit record; classifies the slot
+//               into qA (extension rays) or qB (shadow rays).  Pure traversal.
+//   phase 2  A  extension results: miss -> sky, finished; hit -> absorption, emission MIS, first
+//               NEE sample (shadow ray).
+//            B  shadow results: connect the NEE sample; next NEE sample, or BSDF sample + throughput
+//               update + next extension ray.  Survivors -> next qT, finished paths -> next qF.
 //
 // Regeneration keeps the slots full until the counter runs dry; compaction keeps every stage on
-// full warps regardless of bounce depth or path termination.
+// full warps regardless of bounce depth or path termination.  Several small CTAs share an SM
+// (TB_WF2_CTAS_PER_SM) so that one CTA's barrier wait is filled by the others.
 #pragma once
 
 #ifndef TB_WF2_THREADS
-#define TB_WF2_THREADS 512
+#define TB_WF2_THREADS 256
 #endif
 #ifndef TB_WF2_PATHS
-#define TB_WF2_PATHS 1024
+#define TB_WF2_PATHS 512
 #endif
-#define TB_WF2_MAX_PRIMS 48
-#define TB_WF2_MAX_PAIRS 48
+#ifndef TB_WF2_CTAS_PER_SM
+#define TB_WF2_CTAS_PER_SM 2
+#endif
+#define TB_WF2_MAX_PRIMS 16     // scene tables up to this size are staged in shared memory
+#define TB_WF2_MAX_PAIRS 16
 
 enum { WF2_PH_EXT = 0, WF2_PH_NEE = 1 };
 
@@ -64,15 +69,15 @@ struct Wf2Shared {
     float sumx[TB_WF2_PATHS], sumy[TB_WF2_PATHS], sumz[TB_WF2_PATHS];
     float lax[TB_WF2_PATHS], lay[TB_WF2_PATHS], laz[TB_WF2_PATHS];
     uint32_t cursor[TB_WF2_PATHS];    // slot | prim << 8 | sample << 20
-    // queues
-    uint16_t qT[2][TB_WF2_PATHS];
-    uint16_t qA[TB_WF2_PATHS], qB[TB_WF2_PATHS], qF[TB_WF2_PATHS];
-    int nT[2], nA, nB, nF;
+    // queues (double-buffered by iteration parity where producer and consumer overlap)
+    uint16_t qT[2][TB_WF2_PATHS], qF[2][TB_WF2_PATHS];
+    uint16_t qA[TB_WF2_PATHS], qB[TB_WF2_PATHS];
+    int nT[2], nF[2], nA[2], nB[2];
     int exhausted;
     // scene tables staged on chip
     DPrim prims[TB_WF2_MAX_PRIMS];
     BvhPair pairs[TB_WF2_MAX_PAIRS];
-    FlatNode flat[32];
+    ProgOp flat[32];
 };
 
 // append `slot` to a shared queue for every lane with flag == true: ballot + prefix sum
@@ -160,7 +165,7 @@ TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf
     return true;
 }
 
-__global__ void __launch_bounds__(TB_WF2_THREADS, 1) k_wavefront2(LaunchParams P, unsigned long long total)
+__global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(LaunchParams P, unsigned long long total)
 {
     extern __shared__ __align__(16) unsigned char wf_smem_raw[];
     Wf2Shared& S = *reinterpret_cast<Wf2Shared*>(wf_smem_raw);
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, 1) k_wavefront2(LaunchParams P
         sc.pairs = S.pairs;
     }
     if (sc.numFlat > 0 && sc.numFlat <= 32) {
-        const int words = sc.numFlat * (int)(sizeof(FlatNode) / 4);
+        const int words = sc.numFlat * (int)(sizeof(ProgOp) / 4);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.flat);
         uint32_t* dst = reinterpret_cast<uint32_t*>(S.flat);
         for (int i = tid; i < words; i += TB_WF2_THREADS) dst[i] = src[i];
@@ -191,94 +196,92 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, 1) k_wavefront2(LaunchParams P
     }
     // every slot starts "finished with nothing to splat": stage R fills it with a camera sample
     for (int s = tid; s < TB_WF2_PATHS; s += TB_WF2_THREADS) {
-        S.qF[s] = (uint16_t)s;
+        S.qF[0][s] = (uint16_t)s;
         S.sample[s] = 0xffffffffu;
     }
     if (tid == 0) {
         S.nT[0] = S.nT[1] = 0;
-        S.nA = S.nB = 0;
-        S.nF = TB_WF2_PATHS;
+        S.nF[0] = TB_WF2_PATHS;
+        S.nF[1] = 0;
+        S.nA[0] = S.nA[1] = S.nB[0] = S.nB[1] = 0;
         S.exhausted = 0;
     }
     __syncthreads();
 
     const int maxDepth = P.film.maxDepth;
-    int cur = 0;   // qT[cur] is filled by stages S and R, consumed by stage T
 
-    for (;;) {
-        // ===================== stage R: splat finished samples, regenerate ========================
-        {
-            const int nF = S.nF;
-            for (int q0 = 0; q0 < nF; q0 += TB_WF2_THREADS) {
-                const int q = q0 + tid;
-                const bool active = q < nF;
-                const int s = active ? (int)S.qF[q] : 0;
-                if (active && S.sample[s] != 0xffffffffu) {
-                    int px, py, frame;
-                    decode_sample(P, (unsigned long long)S.sample[s], px, py, frame);
-                    // raster position of the sample: its first two RNG draws (render.cpp:476,481-482)
-                    Rng rr = rng_seed(tb_sample_seed((uint32_t)(py * P.film.width + px), (uint32_t)frame));
-                    float rx = rng_float(rr);
-                    float ry = rng_float(rr);
-                    rx += px;
-                    ry += py;
-                    sample_end(P, px, py, rx, ry, v3(S.Lx[s], S.Ly[s], S.Lz[s]));
-                    S.sample[s] = 0xffffffffu;
+    // Iteration k consumes qT[k&1] / qF[k&1] and produces qT[~k&1] / qF[~k&1]; the counters of
+    // the buffers being produced were cleared by thread 0 during phase 2 of iteration k-1, when
+    // nobody reads or writes them.
+    for (int iter = 0;; ++iter) {
+        const int cur = iter & 1, nxt = cur ^ 1;
+        const int nT = S.nT[cur], nF = S.nF[cur];
+        if (nT == 0 && nF == 0) break;   // uniform: read after the barrier that ended the last phase 2
+
+        // ===================== phase 1 / R: splat finished samples, regenerate =====================
+        for (int q0 = 0; q0 < nF; q0 += TB_WF2_THREADS) {
+            const int q = q0 + tid;
+            const bool active = q < nF;
+            const int s = active ? (int)S.qF[cur][q] : 0;
+            if (active && S.sample[s] != 0xffffffffu) {
+                int px, py, frame;
+                decode_sample(P, (unsigned long long)S.sample[s], px, py, frame);
+                // raster position of the sample: its first two RNG draws (render.cpp:476,481-482)
+                Rng rr = rng_seed(tb_sample_seed((uint32_t)(py * P.film.width + px), (uint32_t)frame));
+                float rx = rng_float(rr);
+                float ry = rng_float(rr);
+                rx += px;
+                ry += py;
+                sample_end(P, px, py, rx, ry, v3(S.Lx[s], S.Ly[s], S.Lz[s]));
+                S.sample[s] = 0xffffffffu;
+            }
+            // claim a new sample; indices on tile padding outside the image are skipped
+            bool want = active && !*(volatile int*)&S.exhausted;
+            bool fresh = false;
+            for (int attempt = 0; attempt < 64; ++attempt) {
+                if (!__any_sync(0xffffffffu, want)) break;
+                const unsigned m = __ballot_sync(0xffffffffu, want);
+                const int lane = tid & 31;
+                const int leader = __ffs(m) - 1;
+                unsigned long long base = 0ull;
+                if (lane == leader) {
+                    base = atomicAdd(P.sampleCounter, (unsigned long long)__popc(m));
+                    if (base + __popc(m) >= total) *(volatile int*)&S.exhausted = 1;
                 }
-                // claim a new sample; indices on tile padding outside the image are skipped
-                bool want = active && !*(volatile int*)&S.exhausted;
-                bool fresh = false;
-                for (int attempt = 0; attempt < 64; ++attempt) {
-                    if (!__any_sync(0xffffffffu, want)) break;
-                    const unsigned m = __ballot_sync(0xffffffffu, want);
-                    const int lane = tid & 31;
-                    const int leader = __ffs(m) - 1;
-                    unsigned long long base = 0ull;
-                    if (lane == leader) {
-                        base = atomicAdd(P.sampleCounter, (unsigned long long)__popc(m));
-                        if (base + __popc(m) >= total) *(volatile int*)&S.exhausted = 1;
-                    }
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    const unsigned long long idx = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
-                    if (want) {
-                        if (idx >= total) {
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const unsigned long long idx = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+                if (want) {
+                    if (idx >= total) {
+                        want = false;
+                    } else {
+                        int px, py, frame;
+                        if (decode_sample(P, idx, px, py, frame)) {
+                            PathState ps;
+                            float rx, ry;
+                            sample_begin(P, px, py, frame, ps, rx, ry);
+                            S.ox[s] = ps.o.x; S.oy[s] = ps.o.y; S.oz[s] = ps.o.z;
+                            S.dx[s] = ps.d.x; S.dy[s] = ps.d.y; S.dz[s] = ps.d.z;
+                            S.time[s] = ps.time;
+                            S.Tx[s] = 1.0f; S.Ty[s] = 1.0f; S.Tz[s] = 1.0f;
+                            S.Lx[s] = 0.0f; S.Ly[s] = 0.0f; S.Lz[s] = 0.0f;
+                            S.eta[s] = 1.0f;
+                            S.ax[s] = 0.0f; S.ay[s] = 0.0f; S.az[s] = 0.0f;
+                            S.bsdfPdf[s] = 1.0f;
+                            S.rng1[s] = ps.rng.s1;
+                            S.rng2[s] = ps.rng.s2;
+                            S.sample[s] = (uint32_t)idx;
+                            S.flags[s] = ((uint32_t)TB_REFLECTED << 1) | ((uint32_t)WF2_PH_EXT << 3);
+                            fresh = true;
                             want = false;
-                        } else {
-                            int px, py, frame;
-                            if (decode_sample(P, idx, px, py, frame)) {
-                                PathState ps;
-                                float rx, ry;
-                                sample_begin(P, px, py, frame, ps, rx, ry);
-                                S.ox[s] = ps.o.x; S.oy[s] = ps.o.y; S.oz[s] = ps.o.z;
-                                S.dx[s] = ps.d.x; S.dy[s] = ps.d.y; S.dz[s] = ps.d.z;
-                                S.time[s] = ps.time;
-                                S.Tx[s] = 1.0f; S.Ty[s] = 1.0f; S.Tz[s] = 1.0f;
-                                S.Lx[s] = 0.0f; S.Ly[s] = 0.0f; S.Lz[s] = 0.0f;
-                                S.eta[s] = 1.0f;
-                                S.ax[s] = 0.0f; S.ay[s] = 0.0f; S.az[s] = 0.0f;
-                                S.bsdfPdf[s] = 1.0f;
-                                S.rng1[s] = ps.rng.s1;
-                                S.rng2[s] = ps.rng.s2;
-                                S.sample[s] = (uint32_t)idx;
-                                S.flags[s] = ((uint32_t)TB_REFLECTED << 1) | ((uint32_t)WF2_PH_EXT << 3);
-                                fresh = true;
-                                want = false;
-                            }
                         }
                     }
                 }
-                wf2_push(S.qT[cur], &S.nT[cur], fresh, s);
             }
-        }
-        __syncthreads();
-        const int nT = S.nT[cur];
-        if (nT == 0) break;   // nothing alive and nothing left to regenerate
-        if (tid == 0) {
-            S.nF = 0;
-            S.nT[cur ^ 1] = 0;
+            // regenerated paths join the NEXT trace queue: no barrier between R and T
+            wf2_push(S.qT[nxt], &S.nT[nxt], fresh, s);
         }
 
-        // ===================== stage T: trace every pending ray ===================================
+        // ===================== phase 1 / T: trace every pending ray ================================
         for (int q0 = 0; q0 < nT; q0 += TB_WF2_THREADS) {
             const int q = q0 + tid;
             const bool active = q < nT;
@@ -310,19 +313,20 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, 1) k_wavefront2(LaunchParams P
                     isNee = true;
                 }
             }
-            wf2_push(S.qA, &S.nA, isExt, s);
-            wf2_push(S.qB, &S.nB, isNee, s);
+            wf2_push(S.qA, &S.nA[cur], isExt, s);
+            wf2_push(S.qB, &S.nB[cur], isNee, s);
         }
         __syncthreads();
-        const int nA = S.nA, nB = S.nB;
-        cur ^= 1;   // stages S and R fill the other qT
-        __syncthreads();
+        const int nA = S.nA[cur], nB = S.nB[cur];
         if (tid == 0) {
-            S.nA = 0;
-            S.nB = 0;
+            // buffers consumed in phase 1 become the production targets of the next iteration
+            S.nT[cur] = 0;
+            S.nF[cur] = 0;
+            S.nA[nxt] = 0;
+            S.nB[nxt] = 0;
         }
 
-        // ===================== stage S/A: extension-ray results ===================================
+        // ===================== phase 2 / A: extension-ray results ==================================
         for (int q0 = 0; q0 < nA; q0 += TB_WF2_THREADS) {
             const int q = q0 + tid;
             const bool active = q < nA;
@@ -382,11 +386,11 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, 1) k_wavefront2(LaunchParams P
                     }
                 }
             }
-            wf2_push(S.qT[cur], &S.nT[cur], cont, s);
-            wf2_push(S.qF, &S.nF, fin, s);
+            wf2_push(S.qT[nxt], &S.nT[nxt], cont, s);
+            wf2_push(S.qF[nxt], &S.nF[nxt], fin, s);
         }
 
-        // ===================== stage S/B: shadow-ray results =======================================
+        // ===================== phase 2 / B: shadow-ray results ======================================
         for (int q0 = 0; q0 < nB; q0 += TB_WF2_THREADS) {
             const int q = q0 + tid;
             const bool active = q < nB;
@@ -431,8 +435,8 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, 1) k_wavefront2(LaunchParams P
                     fin = !cont;
                 }
             }
-            wf2_push(S.qT[cur], &S.nT[cur], cont, s);
-            wf2_push(S.qF, &S.nF, fin, s);
+            wf2_push(S.qT[nxt], &S.nT[nxt], cont, s);
+            wf2_push(S.qF[nxt], &S.nF[nxt], fin, s);
         }
         __syncthreads();
     }
@@ -448,9 +452,15 @@ void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, u
         configured = true;
     }
     cudaMemsetAsync(p.sampleCounter, 0, sizeof(unsigned long long), stream);
-    // one resident CTA per SM; small jobs use fewer CTAs so that every CTA has a full slot array
+    // TB_WF2_CTAS_PER_SM resident CTAs per SM; small jobs use fewer so that every CTA has a full slot array
     unsigned long long want = (total + TB_WF2_PATHS - 1) / TB_WF2_PATHS;
-    int grid = numSMs > 0 ? numSMs : 148;
+    static int ctasPerSM = 0;
+    if (ctasPerSM == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_wavefront2, TB_WF2_THREADS, sizeof(Wf2Shared)) != cudaSuccess ||
+            ctasPerSM < 1)
+            ctasPerSM = 1;
+    }
+    int grid = (numSMs > 0 ? numSMs : 148) * ctasPerSM;
     if (want < (unsigned long long)grid) grid = (int)want;
     if (grid < 1) grid = 1;
     k_wavefront2<<<grid, TB_WF2_THREADS, sizeof(Wf2Shared), stream>>>(p, total);
