@@ -8,33 +8,35 @@
 // wavefront.cu:765-796,1357-1375) would make queue traffic, not the scene, the HBM consumer; here
 // HBM only sees scene misses and the framebuffer reductions.
 //
-// Every slot that is alive has exactly one pending ray: its extension ray or one shadow ray.  Each
-// CTA alternates between two phases separated by __syncthreads(), every stage running over a queue
-// compacted with warp ballot + prefix sum (one shared atomic per warp):
+// Every slot that is alive has exactly one pending ray: its extension ray or one shadow ray, and
+// sits in exactly one of four CTA-shared stage queues.  There are NO block-wide barriers in the
+// main loop: each WARP independently claims a chunk of up to 32 entries from a stage queue,
+// processes it and appends the slots to the queues of their next stages:
 //
-//   phase 1  R  finish + regenerate (queue qF): splat the finished sample into the accumulator,
-//               claim a new sample index from the global counter (one atomic per warp), generate
-//               its camera ray.
-//            T  trace every pending ray (queue qT): closest hit -> hit record; classifies the slot
-//               into qA (extension rays) or qB (shadow rays).  Pure traversal.
-//   phase 2  A  extension results: miss -> sky, finished; hit -> absorption, emission MIS, first
-//               NEE sample (shadow ray).
-//            B  shadow results: connect the NEE sample; next NEE sample, or BSDF sample + throughput
-//               update + next extension ray.  Survivors -> next qT, finished paths -> next qF.
+//   R  finish + regenerate: splat the finished sample into the accumulator, claim a new sample
+//      index from the global counter (one atomic per warp), generate its camera ray      -> T
+//   T  trace the pending ray: closest hit -> hit record                        -> A (extension) / B (shadow)
+//   A  extension result: miss -> sky -> R; hit -> absorption, emission MIS, first NEE sample -> T
+//   B  shadow result: connect the NEE sample; next NEE sample -> T, or BSDF sample, throughput
+//      update and next extension ray -> T, or termination -> R
 //
-// Regeneration keeps the slots full until the counter runs dry; compaction keeps every stage on
-// full warps regardless of bounce depth or path termination.  Several small CTAs share an SM
-// (TB_WF2_CTAS_PER_SM) so that one CTA's barrier wait is filled by the others.
+// The queues are lock-free rings in shared memory: producers reserve cells with one warp-
+// aggregated atomicAdd on `tail` (ballot + prefix sum) and store lap-tagged slot ids; a consumer
+// warp reads the cells optimistically and takes ownership with one compare-and-swap on `head`,
+// so a chunk is always full while the queue holds >= 32 entries (compaction is implicit in the
+// queue).  Regeneration keeps the slots populated until the sample counter runs dry; the CTA
+// exits when its last slot dies.  Warps never wait for each other, so the divergent cost of
+// individual rays or shading branches no longer stalls the rest of the SM.
 #pragma once
 
 #ifndef TB_WF2_THREADS
-#define TB_WF2_THREADS 256
+#define TB_WF2_THREADS 512
 #endif
 #ifndef TB_WF2_PATHS
-#define TB_WF2_PATHS 512
+#define TB_WF2_PATHS 1024      // must be a power of two <= 1024 (10-bit slot ids in the queue cells)
 #endif
 #ifndef TB_WF2_CTAS_PER_SM
-#define TB_WF2_CTAS_PER_SM 2
+#define TB_WF2_CTAS_PER_SM 1
 #endif
 #define TB_WF2_MAX_PRIMS 16     // scene tables up to this size are staged in shared memory
 #define TB_WF2_MAX_PAIRS 16
@@ -69,10 +71,10 @@ struct Wf2Shared {
     float sumx[TB_WF2_PATHS], sumy[TB_WF2_PATHS], sumz[TB_WF2_PATHS];
     float lax[TB_WF2_PATHS], lay[TB_WF2_PATHS], laz[TB_WF2_PATHS];
     uint32_t cursor[TB_WF2_PATHS];    // slot | prim << 8 | sample << 20
-    // queues (double-buffered by iteration parity where producer and consumer overlap)
-    uint16_t qT[2][TB_WF2_PATHS], qF[2][TB_WF2_PATHS];
-    uint16_t qA[TB_WF2_PATHS], qB[TB_WF2_PATHS];
-    int nT[2], nF[2], nA[2], nB[2];
+    // stage queues: rings of lap-tagged slot ids
+    uint16_t ring[4][TB_WF2_PATHS];
+    unsigned int head[4], tail[4];
+    int live;                         // slots that still hold (or may still receive) a path
     int exhausted;
     // scene tables staged on chip
     DPrim prims[TB_WF2_MAX_PRIMS];
@@ -80,17 +82,70 @@ struct Wf2Shared {
     ProgOp flat[32];
 };
 
-// append `slot` to a shared queue for every lane with flag == true: ballot + prefix sum
-TB_DEV void wf2_push(uint16_t* queue, int* count, bool flag, int slot)
+enum { WF2_Q_R = 0, WF2_Q_T = 1, WF2_Q_A = 2, WF2_Q_B = 3 };
+#define WF2_MASK (TB_WF2_PATHS - 1)
+#define WF2_LOG2_PATHS (TB_WF2_PATHS == 1024 ? 10 : TB_WF2_PATHS == 512 ? 9 : TB_WF2_PATHS == 256 ? 8 : 7)
+
+// cell value of ring index i holding slot s: the lap tag (1..63, never 0) makes "reserved but not
+// yet written" and "left over from the previous lap" distinguishable from the expected entry
+TB_DEV uint16_t wf2_cell(unsigned int index, int slot)
+{
+    const unsigned int lap = ((index >> WF2_LOG2_PATHS) % 63u) + 1u;
+    return (uint16_t)((unsigned)slot | (lap << 10));
+}
+
+// append `slot` to stage queue q for every lane with flag == true: ballot + prefix sum, one shared
+// atomic per warp.  The caller has fenced its slot-state writes (__threadfence_block).
+TB_DEV void wf2_push(Wf2Shared& S, int q, bool flag, int slot)
 {
     const unsigned m = __ballot_sync(0xffffffffu, flag);
     if (m == 0u) return;
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(count, __popc(m));
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&S.tail[q], (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (flag) queue[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)slot;
+    if (flag) {
+        const unsigned int idx = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+        *(volatile uint16_t*)&S.ring[q][idx & WF2_MASK] = wf2_cell(idx, slot);
+    }
+}
+
+// Claim up to 32 entries of queue q for this warp.  Returns the number claimed (warp-uniform);
+// lane i < n receives its slot.  Lock-free: cells are read first, ownership is taken with a CAS
+// on head, so a stalled warp can never read a cell that a producer has already recycled.
+TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot)
+{
+    const int lane = threadIdx.x & 31;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        unsigned int h = 0, t = 0;
+        if (lane == 0) {
+            h = *(volatile unsigned int*)&S.head[q];
+            t = *(volatile unsigned int*)&S.tail[q];
+        }
+        h = __shfl_sync(0xffffffffu, h, 0);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        int n = (int)(t - h);
+        if (n < minCount) return 0;
+        if (n > 32) n = 32;
+        // optimistic read; entries reserved by a producer but not yet stored end the chunk early
+        const unsigned int idx = h + (unsigned)lane;
+        const uint16_t cell = *(volatile uint16_t*)&S.ring[q][idx & WF2_MASK];
+        const bool ok = lane < n && (cell >> 10) == (((idx >> WF2_LOG2_PATHS) % 63u) + 1u);
+        const unsigned good = __ballot_sync(0xffffffffu, ok);
+        n = __ffs(~good) - 1;   // length of the valid prefix (32 if all lanes are valid: ~good == 0 -> ffs 0 -> -1)
+        if (good == 0xffffffffu) n = 32;
+        if (n <= 0) continue;
+        unsigned int got = 0;
+        if (lane == 0) got = atomicCAS(&S.head[q], h, h + (unsigned)n);
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (got == h) {
+            __threadfence_block();   // the producer's state writes precede its cell store
+            slot = (int)(cell & 1023u);
+            return n;
+        }
+    }
+    return 0;
 }
 
 TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s)
@@ -194,35 +249,46 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
         for (int i = tid; i < words; i += TB_WF2_THREADS) dst[i] = src[i];
         sc.flat = S.flat;
     }
-    // every slot starts "finished with nothing to splat": stage R fills it with a camera sample
+    // every slot starts in the R queue "finished with nothing to splat": stage R fills it with a
+    // camera sample
     for (int s = tid; s < TB_WF2_PATHS; s += TB_WF2_THREADS) {
-        S.qF[0][s] = (uint16_t)s;
+        S.ring[WF2_Q_R][s] = wf2_cell((unsigned)s, s);
+        S.ring[WF2_Q_T][s] = 0;
+        S.ring[WF2_Q_A][s] = 0;
+        S.ring[WF2_Q_B][s] = 0;
         S.sample[s] = 0xffffffffu;
     }
     if (tid == 0) {
-        S.nT[0] = S.nT[1] = 0;
-        S.nF[0] = TB_WF2_PATHS;
-        S.nF[1] = 0;
-        S.nA[0] = S.nA[1] = S.nB[0] = S.nB[1] = 0;
+        for (int q = 0; q < 4; ++q) S.head[q] = S.tail[q] = 0u;
+        S.tail[WF2_Q_R] = TB_WF2_PATHS;
+        S.live = TB_WF2_PATHS;
         S.exhausted = 0;
     }
-    __syncthreads();
+    __syncthreads();   // the only block-wide barrier: from here on warps run independently
 
     const int maxDepth = P.film.maxDepth;
+    const int lane = tid & 31;
 
-    // Iteration k consumes qT[k&1] / qF[k&1] and produces qT[~k&1] / qF[~k&1]; the counters of
-    // the buffers being produced were cleared by thread 0 during phase 2 of iteration k-1, when
-    // nobody reads or writes them.
-    for (int iter = 0;; ++iter) {
-        const int cur = iter & 1, nxt = cur ^ 1;
-        const int nT = S.nT[cur], nF = S.nF[cur];
-        if (nT == 0 && nF == 0) break;   // uniform: read after the barrier that ended the last phase 2
+    for (;;) {
+        // ---- pick a stage: full chunks first (shade before trace before regenerate, so that
+        // slots flow towards completion), then whatever is left --------------------------------
+        int s = 0, n = 0, stage = -1;
+        for (int pass = 0; pass < 2 && stage < 0; ++pass) {
+            const int need = pass == 0 ? 32 : 1;
+            if ((n = wf2_claim(S, WF2_Q_B, need, s)) > 0) stage = WF2_Q_B;
+            else if ((n = wf2_claim(S, WF2_Q_A, need, s)) > 0) stage = WF2_Q_A;
+            else if ((n = wf2_claim(S, WF2_Q_T, need, s)) > 0) stage = WF2_Q_T;
+            else if ((n = wf2_claim(S, WF2_Q_R, need, s)) > 0) stage = WF2_Q_R;
+        }
+        if (stage < 0) {
+            if (*(volatile int*)&S.live <= 0) break;
+            __nanosleep(200);
+            continue;
+        }
+        const bool active = lane < n;
 
-        // ===================== phase 1 / R: splat finished samples, regenerate =====================
-        for (int q0 = 0; q0 < nF; q0 += TB_WF2_THREADS) {
-            const int q = q0 + tid;
-            const bool active = q < nF;
-            const int s = active ? (int)S.qF[cur][q] : 0;
+        if (stage == WF2_Q_R) {
+            // ===================== R: splat the finished sample, regenerate =======================
             if (active && S.sample[s] != 0xffffffffu) {
                 int px, py, frame;
                 decode_sample(P, (unsigned long long)S.sample[s], px, py, frame);
@@ -241,7 +307,6 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
             for (int attempt = 0; attempt < 64; ++attempt) {
                 if (!__any_sync(0xffffffffu, want)) break;
                 const unsigned m = __ballot_sync(0xffffffffu, want);
-                const int lane = tid & 31;
                 const int leader = __ffs(m) - 1;
                 unsigned long long base = 0ull;
                 if (lane == leader) {
@@ -277,15 +342,13 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                     }
                 }
             }
-            // regenerated paths join the NEXT trace queue: no barrier between R and T
-            wf2_push(S.qT[nxt], &S.nT[nxt], fresh, s);
-        }
-
-        // ===================== phase 1 / T: trace every pending ray ================================
-        for (int q0 = 0; q0 < nT; q0 += TB_WF2_THREADS) {
-            const int q = q0 + tid;
-            const bool active = q < nT;
-            const int s = active ? (int)S.qT[cur][q] : 0;
+            __threadfence_block();
+            wf2_push(S, WF2_Q_T, fresh, s);
+            // slots that could not be refilled die: the CTA exits when none is left
+            const unsigned dead = __ballot_sync(0xffffffffu, active && !fresh);
+            if (dead && lane == 0) atomicSub(&S.live, __popc(dead));
+        } else if (stage == WF2_Q_T) {
+            // ===================== T: trace the pending ray =======================================
             bool isExt = false, isNee = false;
             if (active) {
                 const uint32_t fl = S.flags[s];
@@ -305,32 +368,19 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                 } else {
                     // shadow ray from the surface point: origin = p + FaceForward(n, wi)*eps (render.cpp:121,170)
                     const V3 p = o + d * S.ht[s];
-                    const V3 n = v3(S.hnx[s], S.hny[s], S.hnz[s]);
+                    const V3 nn = v3(S.hnx[s], S.hny[s], S.hnz[s]);
                     const V3 wi = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
-                    const Hit h = trace_closest(sc, p + face_forward(n, wi) * TB_RAY_EPS, wi, time, false);
+                    const Hit h = trace_closest(sc, p + face_forward(nn, wi) * TB_RAY_EPS, wi, time, false);
                     S.st[s] = h.t;
                     S.sprim[s] = h.prim;
                     isNee = true;
                 }
             }
-            wf2_push(S.qA, &S.nA[cur], isExt, s);
-            wf2_push(S.qB, &S.nB[cur], isNee, s);
-        }
-        __syncthreads();
-        const int nA = S.nA[cur], nB = S.nB[cur];
-        if (tid == 0) {
-            // buffers consumed in phase 1 become the production targets of the next iteration
-            S.nT[cur] = 0;
-            S.nF[cur] = 0;
-            S.nA[nxt] = 0;
-            S.nB[nxt] = 0;
-        }
-
-        // ===================== phase 2 / A: extension-ray results ==================================
-        for (int q0 = 0; q0 < nA; q0 += TB_WF2_THREADS) {
-            const int q = q0 + tid;
-            const bool active = q < nA;
-            const int s = active ? (int)S.qA[q] : 0;
+            __threadfence_block();
+            wf2_push(S, WF2_Q_A, isExt, s);
+            wf2_push(S, WF2_Q_B, isNee, s);
+        } else if (stage == WF2_Q_A) {
+            // ===================== A: extension-ray results =======================================
             bool cont = false, fin = false;
             if (active) {
                 const uint32_t fl = S.flags[s];
@@ -386,15 +436,11 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                     }
                 }
             }
-            wf2_push(S.qT[nxt], &S.nT[nxt], cont, s);
-            wf2_push(S.qF[nxt], &S.nF[nxt], fin, s);
-        }
-
-        // ===================== phase 2 / B: shadow-ray results ======================================
-        for (int q0 = 0; q0 < nB; q0 += TB_WF2_THREADS) {
-            const int q = q0 + tid;
-            const bool active = q < nB;
-            const int s = active ? (int)S.qB[q] : 0;
+            __threadfence_block();
+            wf2_push(S, WF2_Q_T, cont, s);
+            wf2_push(S, WF2_Q_R, fin, s);
+        } else {
+            // ===================== B: shadow-ray results ==========================================
             bool cont = false, fin = false;
             if (active) {
                 const uint32_t fl = S.flags[s];
@@ -435,10 +481,10 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                     fin = !cont;
                 }
             }
-            wf2_push(S.qT[nxt], &S.nT[nxt], cont, s);
-            wf2_push(S.qF[nxt], &S.nF[nxt], fin, s);
+            __threadfence_block();
+            wf2_push(S, WF2_Q_T, cont, s);
+            wf2_push(S, WF2_Q_R, fin, s);
         }
-        __syncthreads();
     }
 }
 
