@@ -38,7 +38,7 @@ TB_DEV float filter_gaussian(const DFilm& f, float x)
 {
     const float arg = -f.filterFalloff * x * x;
     if (arg < f.filterArgZero) return 0.0f;   // Max(0, expf(arg) - offset) with expf(arg) < offset
-    return tb_max(0.0f, tbm_expf(arg) - f.filterOffset);
+    return tb_max(0.0f, tb_expf(arg) - f.filterOffset);
 }
 
 // one 16-byte vector reduction per touched pixel (sm_90+: red.global.add.v4.f32)

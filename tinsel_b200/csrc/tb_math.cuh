@@ -103,7 +103,12 @@ TB_HD V3 inverse_transform_vector(const Xf& t, V3 v) { return (1.0f / t.s) * rot
 TB_HD V3 inverse_transform_point(const Xf& t, V3 v) { return (1.0f / t.s) * rotate(qconj(t.r), v - t.p); }
 
 // maths.h:1566-1569 with Quat Lerp (maths.h:79-83 over Quat ops) and Normalize(Quat) (maths.h:547-553)
-TB_HD Xf interpolate_transform(const Xf& a, const Xf& b, float t)
+#if defined(__CUDA_ARCH__)
+#define TB_COLD __noinline__   // rarely executed on the device: keep a single out-of-line copy
+#else
+#define TB_COLD
+#endif
+static __host__ __device__ TB_COLD Xf interpolate_transform(const Xf& a, const Xf& b, float t)
 {
     Xf r;
     r.p = a.p + (b.p - a.p) * t;
@@ -158,6 +163,12 @@ TB_DEV uint32_t tb_sample_seed(uint32_t pixel, uint32_t frame)
     return tb_mix32(h ^ (frame * 0x85EBCA6Bu + 0xC2B2AE35u));
 }
 
+// Out-of-line device copies of the double-precision transcendentals: they are called from a dozen
+// sites and inlining every copy bloats the kernel far past the instruction cache.
+#define TB_NOINLINE static __device__ __noinline__
+TB_NOINLINE void tb_sincosf(float x, float* s, float* c) { tbm_sincosf(x, s, c); }
+TB_NOINLINE float tb_expf(float x) { return tbm_expf(x); }
+
 #define TB_PI 3.141592653589793f
 #define TB_2PI (3.141592653589793f * 2.0f)
 #define TB_INV_PI (1.0f / TB_PI)
@@ -185,7 +196,7 @@ TB_DEV V3 uniform_sample_sphere(float u1, float u2)
     const float r = sqrtf(tb_max(0.f, 1.f - z * z));
     const float phi = 2.f * TB_PI * u2;
     float s, c;
-    tbm_sincosf(phi, &s, &c);
+    tb_sincosf(phi, &s, &c);
     return v3(r * c, r * s, z);
 }
 
@@ -196,7 +207,7 @@ TB_DEV V3 uniform_sample_hemisphere(Rng& rng)
     const float w = sqrtf(1.0f - z * z);
     const float phi = TB_2PI * rng_float(rng);
     float s, c;
-    tbm_sincosf(phi, &s, &c);
+    tb_sincosf(phi, &s, &c);
     return v3(c * w, s * w, z);
 }
 
@@ -206,7 +217,7 @@ TB_DEV V3 cosine_sample_hemisphere(float u1, float u2)
     const float r = sqrtf(u1);
     const float theta = TB_2PI * u2;
     float s, c;
-    tbm_sincosf(theta, &s, &c);
+    tb_sincosf(theta, &s, &c);
     const float sx = r * c, sy = r * s;
     const float z = sqrtf(tb_max(0.0f, 1.0f - sx * sx - sy * sy));
     return v3(sx, sy, z);

@@ -168,7 +168,7 @@ struct MeshHit {
 };
 
 // IntersectRayMesh + MeshQuery, intersection.h:629-749
-TB_DEV bool ray_mesh(const DMesh& m, V3 origin, V3 dir, MeshHit& out)
+static __device__ __noinline__ bool ray_mesh(const DMesh& m, V3 origin, V3 dir, MeshHit& out)
 {
     V3 rcp;
     rcp.x = 1.0f / dir.x;

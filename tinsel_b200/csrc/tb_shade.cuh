@@ -46,7 +46,7 @@ TB_DEV float smith_ggx(float NDotv, float alphaG)
 }
 
 // Fr, disney.h:79-96
-TB_DEV float fresnel_dielectric(float VDotN, float etaI, float etaT)
+TB_NOINLINE float fresnel_dielectric(float VDotN, float etaI, float etaT)
 {
     const float SinThetaT2 = tb_sqr(etaI / etaT) * (1.0f - VDotN * VDotN);
     if (SinThetaT2 > 1.0f) return 1.0f;
@@ -150,6 +150,13 @@ TB_DEV V3 bsdf_eval(const DMaterial& mat, float etaI, float etaO, V3 N, V3 V, V3
     return tb_lerp(brdf, bsdf, mat.transmission);
 }
 
+// BSDFPdf + BSDFEval for the same (V, L): one out-of-line copy serves NEE and the BSDF sample
+TB_NOINLINE void bsdf_eval_pdf(const DMaterial& mat, float etaI, float etaO, V3 N, V3 V, V3 L, V3* f, float* pdf)
+{
+    *pdf = bsdf_pdf(mat, etaI, etaO, N, V, L);
+    *f = bsdf_eval(mat, etaI, etaO, N, V, L);
+}
+
 // the GGX half-vector lobe shared by both branches of BSDFSample, disney.h:183-205 / 256-279;
 // sinPhiHalf / cosPhiHalf = sinf / cosf(r1*k2Pi) are computed by the caller
 TB_DEV V3 sample_ggx_reflection(const DMaterial& mat, float r2, float sinPhiHalf, float cosPhiHalf, V3 U, V3 Vt, V3 N, V3 view)
@@ -167,8 +174,10 @@ TB_DEV V3 sample_ggx_reflection(const DMaterial& mat, float r2, float sinPhiHalf
 // The three lobes that need sinf/cosf of an angle (GGX: r1*k2Pi, cosine: k2Pi*r2, uniform
 // hemisphere: k2Pi*Randf) first only pick their angle; one shared sincos call then serves all
 // lanes of the warp instead of three divergent ones (same values: the product is commutative).
-TB_DEV void bsdf_sample(const DMaterial& mat, float etaI, float etaO, V3 U, V3 Vt, V3 N, V3 view, V3& light, float& pdf,
-                        int& type, Rng& rng)
+// Returns true when the pdf is BSDFPdf(light) (the caller evaluates it together with BSDFEval);
+// false when `pdf` is already final (specular refraction, or 0 for total internal reflection).
+TB_DEV bool bsdf_sample_dir(const DMaterial& mat, float etaI, float etaO, V3 U, V3 Vt, V3 N, V3 view, V3& light, float& pdf,
+                            int& type, Rng& rng)
 {
     enum { LOBE_GGX, LOBE_COSINE, LOBE_UNIFORM };
     int lobe;
@@ -186,10 +195,10 @@ TB_DEV void bsdf_sample(const DMaterial& mat, float etaI, float etaO, V3 U, V3 V
             if (refract_dir(view, N, eta, light)) {
                 type = TB_SPECULAR;
                 pdf = (1.0f - F) * mat.transmission;
-                return;
+                return false;
             }
             pdf = 0.0f;
-            return;
+            return false;
         }
     } else {
         r1 = rng_float(rng);
@@ -213,7 +222,7 @@ TB_DEV void bsdf_sample(const DMaterial& mat, float etaI, float etaO, V3 U, V3 V
         }
     }
     float sn, cs;
-    tbm_sincosf(angleArg * TB_2PI, &sn, &cs);
+    tb_sincosf(angleArg * TB_2PI, &sn, &cs);
     if (lobe == LOBE_GGX) {
         light = sample_ggx_reflection(mat, r2, sn, cs, U, Vt, N, view);
     } else if (lobe == LOBE_COSINE) {
@@ -227,13 +236,13 @@ TB_DEV void bsdf_sample(const DMaterial& mat, float etaI, float etaO, V3 U, V3 V
         const float dx = cs * w, dy = sn * w;
         light = U * dx + Vt * dy - N * uz;
     }
-    pdf = bsdf_pdf(mat, etaI, etaO, N, view, light);
+    return true;
 }
 
 // ---- probe / sky (probe.h, scene.h:161-181) -------------------------------------------------------
 
-// ProbeDirToUV, probe.h:105-113
-TB_DEV void probe_dir_to_uv(V3 dir, float& u, float& v)
+// ProbeDirToUV, probe.h:105-113 (out of line: the double-precision acos/atan2 are large)
+TB_NOINLINE void probe_dir_to_uv(V3 dir, float& u, float& v)
 {
     const float theta = tbm_acosf(tb_clamp(dir.y, -1.0f, 1.0f));
     const float phi = (dir.x == 0.0f && dir.z == 0.0f) ? 0.0f : tbm_atan2f(dir.z, dir.x);
@@ -250,11 +259,9 @@ TB_DEV V3 probe_eval(const DProbe& pr, float u, float v)
     return v3(c.x, c.y, c.z);
 }
 
-// ProbePdf, probe.h:136-160
-TB_DEV float probe_pdf(const DProbe& pr, V3 d)
+// ProbePdf, probe.h:136-160, given uv = ProbeDirToUV(d)
+TB_DEV float probe_pdf(const DProbe& pr, float u, float v)
 {
-    float u, v;
-    probe_dir_to_uv(d, u, v);
     const int col = tb_clamp(int(u * pr.width), 0, pr.width - 1);
     const int row = tb_clamp(int(v * pr.height), 0, pr.height - 1);
     float pdf = __ldg(&pr.pdfX[row * pr.width + col]) * __ldg(&pr.pdfY[row]);
@@ -300,19 +307,15 @@ TB_DEV void probe_sample(const DProbe& pr, V3& dir, V3& color, float& pdf, Rng& 
     const float theta = v * TB_PI;
     const float phi = u * 2.0f * TB_PI;
     float st, ct, sp, cp;
-    tbm_sincosf(theta, &st, &ct);
-    tbm_sincosf(phi, &sp, &cp);
+    tb_sincosf(theta, &st, &ct);
+    tb_sincosf(phi, &sp, &cp);
     dir = v3(-st * cp, ct, -st * sp);
 }
 
-// Sky::Eval, scene.h:168-178
-TB_DEV V3 sky_eval(const DScene& sc, V3 dir)
+// Sky::Eval, scene.h:168-178, given uv = ProbeDirToUV(dir) when the sky has a probe
+TB_DEV V3 sky_eval(const DScene& sc, V3 dir, float u, float v)
 {
-    if (sc.probe.valid) {
-        float u, v;
-        probe_dir_to_uv(dir, u, v);
-        return probe_eval(sc.probe, u, v);
-    }
+    if (sc.probe.valid) return probe_eval(sc.probe, u, v);
     return tb_lerp(sc.horizon, sc.zenith, sqrtf(tb_abs(dir.y)));
 }
 
@@ -399,12 +402,14 @@ TB_DEV void path_init(PathState& ps, V3 origin, V3 dir, float time, Rng rng)
 TB_DEV void path_miss(const DScene& sc, PathState& ps, int bounce)
 {
     float weight = 1.0f;
+    float u = 0.0f, v = 0.0f;
+    if (sc.probe.valid) probe_dir_to_uv(ps.d, u, v);   // shared by ProbePdf and Sky::Eval (both call ProbeDirToUV(rayDir))
     if (sc.probe.valid && bounce > 0 && ps.rayType != TB_SPECULAR) {
-        const float skyPdf = probe_pdf(sc.probe, ps.d);
+        const float skyPdf = probe_pdf(sc.probe, u, v);
         const float cbsdf = 0.5f, csky = 0.5f;   // kBsdfSamples/N, kProbeSamples/N with N = 2
         weight = cbsdf * ps.bsdfPdf / (cbsdf * ps.bsdfPdf + csky * skyPdf);
     }
-    ps.L = ps.L + weight * sky_eval(sc, ps.d) * ps.T;
+    ps.L = ps.L + weight * sky_eval(sc, ps.d, u, v) * ps.T;
 }
 
 // Hit prologue, render.cpp:255-310: medium bookkeeping, Beer-Lambert, emission with MIS.
@@ -422,7 +427,7 @@ TB_DEV void path_hit(const DScene& sc, PathState& ps, const Hit& h, int bounce, 
     // -0*t = -0 and expf(-0) = 1 exactly, so the multiply is the identity and is skipped.
     if (!(ps.absorb.x == 0.0f && ps.absorb.y == 0.0f && ps.absorb.z == 0.0f)) {
         const V3 e = -ps.absorb * h.t;
-        ps.T = ps.T * v3(tbm_expf(e.x), tbm_expf(e.y), tbm_expf(e.z));
+        ps.T = ps.T * v3(tb_expf(e.x), tb_expf(e.y), tb_expf(e.z));
     }
 
     sf.prim = h.prim;
@@ -511,42 +516,44 @@ TB_DEV bool nee_generate(const DScene& sc, const Surface& sf, float time, NeeCur
 TB_DEV void nee_connect(const DScene& sc, const Surface& sf, const ShadowRay& sr, const Hit& sh, NeeCursor& c)
 {
     const DMaterial& mat = sc.prims[sf.prim].mat;
-    if (sr.light < 0) {
-        if (sh.prim < 0) {
-            const float bsdfPdf = bsdf_pdf(mat, sf.etaI, sf.etaO, sf.n, sf.wo, sr.d);
-            const V3 f = bsdf_eval(mat, sf.etaI, sf.etaO, sf.n, sf.wo, sr.d);
-            if (bsdfPdf > 0.0f) {
-                const float cbsdf = 0.5f, csky = 0.5f;
-                const float skyPdf = sr.skyPdf;
-                const float weight = csky * skyPdf / (cbsdf * bsdfPdf + csky * skyPdf);
-                if (weight > 0.0f) c.sum = c.sum + weight * sr.lightN * f * tb_abs(dot(sr.d, sf.n)) / skyPdf;
-            }
+    const bool isProbe = sr.light < 0;
+    // decide first whether BSDFPdf/BSDFEval are needed at all (both are pure), then evaluate them
+    // once for whichever kind of sample this is
+    float nl = 0.0f;
+    bool need;
+    if (isProbe) {
+        need = sh.prim < 0;                                   // unoccluded probe direction, render.cpp:122
+    } else {
+        need = false;
+        if (sh.prim >= 0 && fabsf(sh.t - sr.dist) <= 1.e-2f) {   // render.cpp:176-184
+            nl = tb_abs(dot(sr.lightN, sr.d));
+            need = !(tb_abs(nl) < 1.e-6f);                    // render.cpp:190-191 `continue`
+        }
+    }
+    V3 f = v3s(0.0f);
+    float bsdfPdf = 0.0f;
+    if (need) bsdf_eval_pdf(mat, sf.etaI, sf.etaO, sf.n, sf.wo, sr.d, &f, &bsdfPdf);
+
+    if (isProbe) {
+        if (need && bsdfPdf > 0.0f) {
+            const float cbsdf = 0.5f, csky = 0.5f;
+            const float skyPdf = sr.skyPdf;
+            const float weight = csky * skyPdf / (cbsdf * bsdfPdf + csky * skyPdf);
+            if (weight > 0.0f) c.sum = c.sum + weight * sr.lightN * f * tb_abs(dot(sr.d, sf.n)) / skyPdf;
         }
         // `sum /= float(kProbeSamples)` multiplies by 1.0: no-op
         return;
     }
     const DPrim& light = sc.prims[sr.light];
-    if (sh.prim >= 0) {
-        const float t = sh.t;
-        const float tSq = t * t;
-        if (fabsf(t - sr.dist) <= 1.e-2f) {
-            const float nl = tb_abs(dot(sr.lightN, sr.d));
-            if (!(tb_abs(nl) < 1.e-6f)) {
-                const float lightArea = light.area;
-                const float lightPdf = ((1.0f / lightArea) * tSq) / nl;
-                const float bsdfPdf = bsdf_pdf(mat, sf.etaI, sf.etaO, sf.n, sf.wo, sr.d);
-                const V3 f = bsdf_eval(mat, sf.etaI, sf.etaO, sf.n, sf.wo, sr.d);
-                if (bsdfPdf > 0.0f) {
-                    const int N = int(light.lightSamples + 1.0f);
-                    const float cbsdf = 1.0f / N;
-                    const float clight = float(light.lightSamples) / N;
-                    const float weight = clight * lightPdf / (cbsdf * bsdfPdf + clight * lightPdf);
-                    // emission of whatever the shadow ray hit, not of the sampled light (render.cpp:217)
-                    c.Lacc = c.Lacc + weight * f * sc.prims[sh.prim].mat.emission *
-                                          (tb_abs(dot(sr.d, sf.n)) / tb_max(1.e-3f, lightPdf));
-                }
-            }
-        }
+    if (need && bsdfPdf > 0.0f) {
+        const float tSq = sh.t * sh.t;
+        const float lightPdf = ((1.0f / light.area) * tSq) / nl;
+        const int N = int(light.lightSamples + 1.0f);
+        const float cbsdf = 1.0f / N;
+        const float clight = float(light.lightSamples) / N;
+        const float weight = clight * lightPdf / (cbsdf * bsdfPdf + clight * lightPdf);
+        // emission of whatever the shadow ray hit, not of the sampled light (render.cpp:217)
+        c.Lacc = c.Lacc + weight * f * sc.prims[sh.prim].mat.emission * (tb_abs(dot(sr.d, sf.n)) / tb_max(1.e-3f, lightPdf));
     }
     c.sample++;
     if (c.sample >= light.lightSamples) {
@@ -569,11 +576,17 @@ TB_DEV bool path_scatter(const DScene& sc, PathState& ps, const Surface& sf, V3 
     V3 bsdfDir = v3s(0.0f);
     int bsdfType = TB_REFLECTED;
     float pdf = 0.0f;
-    bsdf_sample(prim.mat, sf.etaI, sf.etaO, u, v, sf.n, sf.wo, bsdfDir, pdf, bsdfType, ps.rng);
+    const bool pdfFromBsdf = bsdf_sample_dir(prim.mat, sf.etaI, sf.etaO, u, v, sf.n, sf.wo, bsdfDir, pdf, bsdfType, ps.rng);
+    V3 f = v3s(0.0f);
+    if (pdfFromBsdf || pdf > 0.0f) {
+        // pdf = BSDFPdf(dir) (disney.h:291) and f = BSDFEval(dir) (render.cpp:341) share one call
+        float p2 = 0.0f;
+        bsdf_eval_pdf(prim.mat, sf.etaI, sf.etaO, sf.n, sf.wo, bsdfDir, &f, &p2);
+        if (pdfFromBsdf) pdf = p2;
+    }
     ps.bsdfPdf = pdf;
     if (pdf <= 0.0f) return false;
 
-    const V3 f = bsdf_eval(prim.mat, sf.etaI, sf.etaO, sf.n, sf.wo, bsdfDir);
     if (dot(bsdfDir, sf.n) <= 0.0f) {
         ps.eta = sf.etaO;
         ps.absorb = sf.outAbsorb;

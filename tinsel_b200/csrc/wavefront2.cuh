@@ -26,7 +26,8 @@
 // so a chunk is always full while the queue holds >= 32 entries (compaction is implicit in the
 // queue).  Regeneration keeps the slots populated until the sample counter runs dry; the CTA
 // exits when its last slot dies.  Warps never wait for each other, so the divergent cost of
-// individual rays or shading branches no longer stalls the rest of the SM.
+// individual rays or shading branches no longer stalls the rest of the SM; a shared stage
+// preference keeps them loosely in step so that they share the instruction cache.
 #pragma once
 
 #ifndef TB_WF2_THREADS
@@ -74,6 +75,7 @@ struct Wf2Shared {
     // stage queues: rings of lap-tagged slot ids
     uint16_t ring[4][TB_WF2_PATHS];
     unsigned int head[4], tail[4];
+    int pref;                         // stage the warps currently prefer (soft phases, see the main loop)
     int live;                         // slots that still hold (or may still receive) a path
     int exhausted;
     // scene tables staged on chip
@@ -82,7 +84,7 @@ struct Wf2Shared {
     ProgOp flat[32];
 };
 
-enum { WF2_Q_R = 0, WF2_Q_T = 1, WF2_Q_A = 2, WF2_Q_B = 3 };
+enum { WF2_Q_T = 0, WF2_Q_A = 1, WF2_Q_B = 2, WF2_Q_R = 3 };   // cyclic order of the stage sweep
 #define WF2_MASK (TB_WF2_PATHS - 1)
 #define WF2_LOG2_PATHS (TB_WF2_PATHS == 1024 ? 10 : TB_WF2_PATHS == 512 ? 9 : TB_WF2_PATHS == 256 ? 8 : 7)
 
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     if (tid == 0) {
         for (int q = 0; q < 4; ++q) S.head[q] = S.tail[q] = 0u;
         S.tail[WF2_Q_R] = TB_WF2_PATHS;
+        S.pref = WF2_Q_R;
         S.live = TB_WF2_PATHS;
         S.exhausted = 0;
     }
@@ -270,16 +273,23 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     const int lane = tid & 31;
 
     for (;;) {
-        // ---- pick a stage: full chunks first (shade before trace before regenerate, so that
-        // slots flow towards completion), then whatever is left --------------------------------
+        // ---- pick a stage.  Warps run independently, but they sweep the stages together: every
+        // warp starts its search at the CTA-wide preferred stage and moves on cyclically
+        // (T -> A -> B -> R -> T) when that queue has no full chunk left, dragging the preference
+        // along.  At any time the warps of a CTA are therefore in at most two adjacent stages and
+        // share their instruction stream (the whole kernel is far larger than the instruction
+        // cache), yet nobody ever waits at a barrier for a slow ray or shading branch. ------------
         int s = 0, n = 0, stage = -1;
-        for (int pass = 0; pass < 2 && stage < 0; ++pass) {
-            const int need = pass == 0 ? 32 : 1;
-            if ((n = wf2_claim(S, WF2_Q_B, need, s)) > 0) stage = WF2_Q_B;
-            else if ((n = wf2_claim(S, WF2_Q_A, need, s)) > 0) stage = WF2_Q_A;
-            else if ((n = wf2_claim(S, WF2_Q_T, need, s)) > 0) stage = WF2_Q_T;
-            else if ((n = wf2_claim(S, WF2_Q_R, need, s)) > 0) stage = WF2_Q_R;
+        int p = 0;
+        if (lane == 0) p = *(volatile int*)&S.pref;
+        p = __shfl_sync(0xffffffffu, p, 0);
+        for (int k = 0; k < 8 && stage < 0; ++k) {
+            // k = 0..3: full chunks only; k = 4..7: whatever is left
+            const int q = (p + k) & 3;
+            n = wf2_claim(S, q, k < 4 ? 32 : 1, s);
+            if (n > 0) stage = q;
         }
+        if (stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
         if (stage < 0) {
             if (*(volatile int*)&S.live <= 0) break;
             __nanosleep(200);
@@ -352,28 +362,31 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
             bool isExt = false, isNee = false;
             if (active) {
                 const uint32_t fl = S.flags[s];
-                const V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
-                const V3 d = v3(S.dx[s], S.dy[s], S.dz[s]);
+                V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
+                V3 d = v3(S.dx[s], S.dy[s], S.dz[s]);
                 const float time = S.time[s];
-                if (((fl >> 3) & 1u) == WF2_PH_EXT) {
-                    if (maxDepth > 0) {
-                        const Hit h = trace_closest(sc, o, d, time, true);
+                isExt = ((fl >> 3) & 1u) == WF2_PH_EXT;
+                isNee = !isExt;
+                if (isNee) {
+                    // shadow ray from the surface point: origin = p + FaceForward(n, wi)*eps (render.cpp:121,170)
+                    const V3 p = o + d * S.ht[s];
+                    const V3 nn = v3(S.hnx[s], S.hny[s], S.hnz[s]);
+                    d = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
+                    o = p + face_forward(nn, d) * TB_RAY_EPS;
+                }
+                if (isNee || maxDepth > 0) {
+                    // one traversal instance serves both ray kinds (normals only for extension rays)
+                    const Hit h = trace_closest(sc, o, d, time, isExt);
+                    if (isExt) {
                         S.ht[s] = h.t;
                         S.hnx[s] = h.n.x; S.hny[s] = h.n.y; S.hnz[s] = h.n.z;
                         S.hprim[s] = h.prim;
                     } else {
-                        S.hprim[s] = -2;   // maxDepth == 0: no trace at all, radiance stays 0
+                        S.st[s] = h.t;
+                        S.sprim[s] = h.prim;
                     }
-                    isExt = true;
                 } else {
-                    // shadow ray from the surface point: origin = p + FaceForward(n, wi)*eps (render.cpp:121,170)
-                    const V3 p = o + d * S.ht[s];
-                    const V3 nn = v3(S.hnx[s], S.hny[s], S.hnz[s]);
-                    const V3 wi = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
-                    const Hit h = trace_closest(sc, p + face_forward(nn, wi) * TB_RAY_EPS, wi, time, false);
-                    S.st[s] = h.t;
-                    S.sprim[s] = h.prim;
-                    isNee = true;
+                    S.hprim[s] = -2;   // maxDepth == 0: no trace at all, radiance stays 0
                 }
             }
             __threadfence_block();
