@@ -281,6 +281,7 @@ struct tb200_renderer {
     void* lastOutput = nullptr;
 
     int pipeline = 2;             // 0 = mega (validation), 2 = wavefront (product)
+    int hardPhases = 1;           // wavefront scheduling mode (see wavefront2.cuh)
     tb200_stats stats;
 };
 
@@ -358,6 +359,16 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
         meshes[m].rootRef = root;
     }
     if (!upload(meshes, &r->dMeshes, h2d)) return false;
+    // Scheduling mode of the wavefront kernel: free-running warps when ray cost varies a lot (a deep
+    // mesh BVH), block-synchronous stages otherwise.  TINSEL_B200_SCHED=hard|free overrides.
+    {
+        int maxTris = 0;
+        for (int m = 0; m < s->numMeshes; ++m) maxTris = std::max(maxTris, s->meshes[m].numIndices / 3);
+        r->hardPhases = maxTris > 4096 ? 0 : 1;
+        const char* sched = getenv("TINSEL_B200_SCHED");
+        if (sched && strcmp(sched, "hard") == 0) r->hardPhases = 1;
+        if (sched && strcmp(sched, "free") == 0) r->hardPhases = 0;
+    }
 
     // primitives
     std::vector<DPrim> prims(s->numPrimitives);
@@ -465,6 +476,7 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     }
     P->accum = r->boundAccum ? r->boundAccum : r->dAccum;
     P->sampleCounter = r->dCounter;
+    P->hardPhases = r->hardPhases;
     P->firstRow = 0;
     P->numRows = o->height;
     P->shard = r->shard;

@@ -267,33 +267,54 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
         S.live = TB_WF2_PATHS;
         S.exhausted = 0;
     }
-    __syncthreads();   // the only block-wide barrier: from here on warps run independently
+    __syncthreads();
 
     const int maxDepth = P.film.maxDepth;
     const int lane = tid & 31;
 
+    // Two scheduling modes share the stage code below (P.hardPhases, uniform for the launch):
+    //
+    //  * hard phases: all warps of the CTA work on the same stage, claiming chunks dynamically
+    //    until its queue is empty, then meet at a block barrier and move on (R -> T -> A,B -> R).
+    //    The kernel is far larger than the instruction cache, so warps that execute the same
+    //    code at the same time share every instruction line; this is the faster mode when rays
+    //    cost about the same (small scenes held in shared memory).
+    //  * free running: no barriers at all; every warp picks the next stage itself, starting at a
+    //    CTA-wide preferred stage and moving on cyclically when that queue has no full chunk left
+    //    (dragging the preference along).  Nobody ever waits for a slow ray, which wins when ray
+    //    cost varies wildly (deep mesh BVHs) and the hot loop is small enough to stay cached.
+    const bool hard = P.hardPhases != 0;
+    int phase = WF2_Q_R;
+
     for (;;) {
-        // ---- pick a stage.  Warps run independently, but they sweep the stages together: every
-        // warp starts its search at the CTA-wide preferred stage and moves on cyclically
-        // (T -> A -> B -> R -> T) when that queue has no full chunk left, dragging the preference
-        // along.  At any time the warps of a CTA are therefore in at most two adjacent stages and
-        // share their instruction stream (the whole kernel is far larger than the instruction
-        // cache), yet nobody ever waits at a barrier for a slow ray or shading branch. ------------
         int s = 0, n = 0, stage = -1;
-        int p = 0;
-        if (lane == 0) p = *(volatile int*)&S.pref;
-        p = __shfl_sync(0xffffffffu, p, 0);
-        for (int k = 0; k < 8 && stage < 0; ++k) {
-            // k = 0..3: full chunks only; k = 4..7: whatever is left
-            const int q = (p + k) & 3;
-            n = wf2_claim(S, q, k < 4 ? 32 : 1, s);
-            if (n > 0) stage = q;
-        }
-        if (stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
-        if (stage < 0) {
-            if (*(volatile int*)&S.live <= 0) break;
-            __nanosleep(200);
-            continue;
+        if (hard) {
+            n = wf2_claim(S, phase, 1, s);
+            if (n > 0) {
+                stage = phase;
+            } else {
+                // this stage's queue is drained (nobody pushes into the stage being run)
+                if (phase != WF2_Q_A) __syncthreads();          // A and B touch disjoint slots: no barrier between them
+                if (phase == WF2_Q_R && *(volatile int*)&S.live <= 0) break;   // `live` only changes during R
+                phase = (phase + 1) & 3;
+                continue;
+            }
+        } else {
+            int p = 0;
+            if (lane == 0) p = *(volatile int*)&S.pref;
+            p = __shfl_sync(0xffffffffu, p, 0);
+            for (int k = 0; k < 8 && stage < 0; ++k) {
+                // k = 0..3: full chunks only; k = 4..7: whatever is left
+                const int q = (p + k) & 3;
+                n = wf2_claim(S, q, k < 4 ? 32 : 1, s);
+                if (n > 0) stage = q;
+            }
+            if (stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
+            if (stage < 0) {
+                if (*(volatile int*)&S.live <= 0) break;
+                __nanosleep(200);
+                continue;
+            }
         }
         const bool active = lane < n;
 

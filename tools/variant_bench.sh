@@ -1,8 +1,10 @@
 #!/bin/bash
-# development aid: time alternative builds of the library (TINSEL_B200_LIB) on the headline workload
+# development aid: time alternative builds of the library (TINSEL_B200_LIB) x scheduling modes
 for lib in "$@"; do
-  echo "== $lib"
-  TINSEL_B200_LIB=$PWD/tinsel_b200/$lib python tools/profile_run.py cornell 1024 1024 32 2>&1 | tail -1
-  TINSEL_B200_LIB=$PWD/tinsel_b200/$lib python tools/profile_run.py veach 1024 1024 16 2>&1 | tail -1
-  TINSEL_B200_LIB=$PWD/tinsel_b200/$lib python tools/profile_run.py ajax 1024 1024 16 2>&1 | tail -1
+  for sched in hard free; do
+    echo "== $lib sched=$sched"
+    for sc in "cornell 1024 1024 32" "veach 1024 1024 16" "ajax 1024 1024 16"; do
+      TINSEL_B200_SCHED=$sched TINSEL_B200_LIB=$PWD/tinsel_b200/$lib python tools/profile_run.py $sc 2>&1 | tail -1
+    done
+  done
 done
