@@ -77,15 +77,20 @@ TB_DEV float bsdf_pdf(const DMaterial& mat, float etaI, float etaO, V3 n, V3 V, 
         const float brdfPdf = TB_INV_2PI * mat.subsurface * 0.5f;
         return tb_lerp(brdfPdf, bsdfPdf, mat.transmission);
     }
-    const float F = fresnel_dielectric(dot(n, V), etaI, etaO);
+    const float NV = dot(n, V);
     const float a = mat.alpha;
     const V3 half = safe_normalize(L + V, v3s(0.0f));
     const float cosThetaHalf = tb_abs(dot(half, n));
     const float pdfHalf = gtr2(cosThetaHalf, a) * cosThetaHalf;
     const float pdfSpec = 0.25f * pdfHalf / tb_max(1.e-6f, dot(L, half));
     const float pdfDiff = tb_abs(dot(L, n)) * TB_INV_PI * (1.0f - mat.subsurface);
-    const float bsdfPdf = pdfSpec * F;
     const float brdfPdf = tb_lerp(pdfDiff, pdfSpec, 0.5f);
+    // Lerp(brdfPdf, pdfSpec*F, transmission): with transmission == 0 and a front-facing view the
+    // Fresnel term is finite (both denominators of Fr are positive), so the lerp adds
+    // (finite)*0 = +-0 and returns brdfPdf unchanged; Fr is skipped then.
+    if (mat.transmission == 0.0f && NV > 0.0f) return brdfPdf;
+    const float F = fresnel_dielectric(NV, etaI, etaO);
+    const float bsdfPdf = pdfSpec * F;
     return tb_lerp(brdfPdf, bsdfPdf, mat.transmission);
 }
 

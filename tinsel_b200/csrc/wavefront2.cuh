@@ -119,7 +119,8 @@ TB_DEV void wf2_push(Wf2Shared& S, int q, bool flag, int slot)
 TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot)
 {
     const int lane = threadIdx.x & 31;
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    int notReady = 0;
+    for (;;) {
         unsigned int h = 0, t = 0;
         if (lane == 0) {
             h = *(volatile unsigned int*)&S.head[q];
@@ -135,9 +136,11 @@ TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot)
         const uint16_t cell = *(volatile uint16_t*)&S.ring[q][idx & WF2_MASK];
         const bool ok = lane < n && (cell >> 10) == (((idx >> WF2_LOG2_PATHS) % 63u) + 1u);
         const unsigned good = __ballot_sync(0xffffffffu, ok);
-        n = __ffs(~good) - 1;   // length of the valid prefix (32 if all lanes are valid: ~good == 0 -> ffs 0 -> -1)
-        if (good == 0xffffffffu) n = 32;
-        if (n <= 0) continue;
+        n = (good == 0xffffffffu) ? 32 : __ffs(~good) - 1;   // length of the valid prefix
+        if (n <= 0) {
+            if (++notReady > 8) return 0;   // a producer is between its reservation and its store
+            continue;
+        }
         unsigned int got = 0;
         if (lane == 0) got = atomicCAS(&S.head[q], h, h + (unsigned)n);
         got = __shfl_sync(0xffffffffu, got, 0);
@@ -146,8 +149,24 @@ TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot)
             slot = (int)(cell & 1023u);
             return n;
         }
+        // lost the race to another warp, which made progress: try again
     }
-    return 0;
+}
+
+// Hard-phase variant: while a stage runs nobody pushes into its queue, so `tail` is fixed and a
+// ticket (atomicAdd on head) can never overshoot into entries that do not exist yet.  `head` is
+// put back to `tail` by thread 0 after the barrier that ends the stage.
+TB_DEV int wf2_claim_ticket(Wf2Shared& S, int q, unsigned int tail, int& slot)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(&S.head[q], 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int avail = (int)(tail - base);
+    if (avail <= 0) return 0;
+    const int n = avail < 32 ? avail : 32;
+    if (lane < n) slot = (int)(*(volatile uint16_t*)&S.ring[q][(base + (unsigned)lane) & WF2_MASK] & 1023u);
+    return n;
 }
 
 TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s)
@@ -285,18 +304,21 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     //    cost varies wildly (deep mesh BVHs) and the hot loop is small enough to stay cached.
     const bool hard = P.hardPhases != 0;
     int phase = WF2_Q_R;
+    unsigned int phaseTail = TB_WF2_PATHS;   // every slot starts in the R queue
 
     for (;;) {
         int s = 0, n = 0, stage = -1;
         if (hard) {
-            n = wf2_claim(S, phase, 1, s);
+            n = wf2_claim_ticket(S, phase, phaseTail, s);
             if (n > 0) {
                 stage = phase;
             } else {
                 // this stage's queue is drained (nobody pushes into the stage being run)
                 if (phase != WF2_Q_A) __syncthreads();          // A and B touch disjoint slots: no barrier between them
+                if (tid == 0) S.head[phase] = phaseTail;        // undo the ticket overshoot
                 if (phase == WF2_Q_R && *(volatile int*)&S.live <= 0) break;   // `live` only changes during R
                 phase = (phase + 1) & 3;
+                phaseTail = *(volatile unsigned int*)&S.tail[phase];   // stable until this stage ends
                 continue;
             }
         } else {
