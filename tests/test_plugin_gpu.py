@@ -39,3 +39,40 @@ def test_plugin_render_matches_seeded_oracle(name):
     rel = np.linalg.norm((out - oracle).astype(np.float64)) / np.linalg.norm(oracle.astype(np.float64))
     assert rel <= 1e-4, rel
     ref.close()
+
+
+HEADLESS = os.path.join(tb.ROOT, "tinsel_b200", "plugin", "tinsel_headless")
+HEADLESS_CPU = os.path.join(tb.ROOT, "tinsel_b200", "plugin", "tinsel_headless_cpu")
+
+
+def _png(path):
+    from PIL import Image
+    return np.asarray(Image.open(path).convert("RGB"), dtype=np.float64)
+
+
+@pytest.mark.gpu
+def test_unmodified_tinsel_app_renders_through_the_plugin(tmp_path):
+    """tinsel's OWN application -- src/main.cpp + loader + PNG writer compiled unmodified (only a
+    force-included GL/GLUT shim and -DCreateCpuRenderer=CreateGpuWavefrontRenderer on main.cpp's
+    compile line) -- loads tests/data/mini0.tin in batch mode, renders 64 spp through this repo's
+    renderer and writes the PNG; the same app with tinsel's CpuRenderer is the comparison."""
+    import shutil
+    import subprocess
+    if not (os.path.exists(HEADLESS) and os.path.exists(HEADLESS_CPU)):
+        pytest.skip("headless tinsel app not built (build container only)")
+    os.environ.pop("TINSEL_B200_PIPELINE", None)
+    imgs = {}
+    for name, exe in (("gpu", HEADLESS), ("cpu", HEADLESS_CPU)):
+        d = tmp_path / name
+        d.mkdir()
+        shutil.copy(os.path.join(tb.ROOT, "tests", "data", "mini0.tin"), d / "mini0.tin")
+        # batch mode: renders mini0.tin, writes mini0.tin.png, exits(-1) when mini1.tin is missing (main.cpp:128-132)
+        subprocess.run([exe, "-spp=64", "mini%d.tin"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+        assert (d / "mini0.tin.png").exists(), "%s app wrote no image" % name
+        imgs[name] = _png(str(d / "mini0.tin.png"))
+    g, c = imgs["gpu"], imgs["cpu"]
+    assert g.shape == c.shape == (64, 96, 3)
+    # different RNG streams (the CPU renderer has one sequential stream): compare statistically
+    assert abs(g.mean() - c.mean()) / c.mean() < 0.02
+    blur = lambda a: a.reshape(16, 4, 24, 4, 3).mean(axis=(1, 3))
+    assert np.abs(blur(g) - blur(c)).mean() < 6.0   # 8-bit sRGB units on 4x4 block means
