@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     // Two scheduling modes share the stage code below (P.hardPhases, uniform for the launch):
     //
     //  * hard phases: all warps of the CTA work on the same stage, claiming chunks dynamically
-    //    until its queue is empty, then meet at a block barrier and move on (R -> T -> A,B -> R).
+    //    until its queue is empty, then meet at a block barrier and move on (R -> T -> A -> B -> R).
     //    The kernel is far larger than the instruction cache, so warps that execute the same
     //    code at the same time share every instruction line; this is the faster mode when rays
     //    cost about the same (small scenes held in shared memory).
@@ -313,9 +313,12 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
             if (n > 0) {
                 stage = phase;
             } else {
-                // this stage's queue is drained (nobody pushes into the stage being run)
-                if (phase != WF2_Q_A) __syncthreads();          // A and B touch disjoint slots: no barrier between them
-                if (tid == 0) S.head[phase] = phaseTail;        // undo the ticket overshoot
+                // this stage's queue is drained (nobody pushes into the stage being run).  After the
+                // barrier no warp holds or requests a ticket of this stage any more, so thread 0 can
+                // undo the overshoot of the failed requests (head back to tail) before the stage
+                // comes round again.
+                __syncthreads();
+                if (tid == 0) S.head[phase] = phaseTail;
                 if (phase == WF2_Q_R && *(volatile int*)&S.live <= 0) break;   // `live` only changes during R
                 phase = (phase + 1) & 3;
                 phaseTail = *(volatile unsigned int*)&S.tail[phase];   // stable until this stage ends
