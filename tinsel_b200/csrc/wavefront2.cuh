@@ -73,8 +73,9 @@ struct Wf2Shared {
     float lax[TB_WF2_PATHS], lay[TB_WF2_PATHS], laz[TB_WF2_PATHS];
     uint32_t cursor[TB_WF2_PATHS];    // slot | prim << 8 | sample << 20
     // stage queues: rings of lap-tagged slot ids
-    uint16_t ring[4][TB_WF2_PATHS];
-    unsigned int head[4], tail[4];
+    uint16_t ring[6][TB_WF2_PATHS];
+    unsigned int head[6], tail[6];
+    unsigned int snap[5];             // hard-phase mode: the tail each stage of the current phase runs with
     int pref;                         // stage the warps currently prefer (soft phases, see the main loop)
     int live;                         // slots that still hold (or may still receive) a path
     int exhausted;
@@ -84,7 +85,9 @@ struct Wf2Shared {
     ProgOp flat[32];
 };
 
-enum { WF2_Q_T = 0, WF2_Q_A = 1, WF2_Q_B = 2, WF2_Q_R = 3 };   // cyclic order of the stage sweep
+// stage queues.  T, A, B, R in the cyclic order of the free-running sweep; F0/F1 hold the freshly
+// regenerated camera rays in hard-phase mode (double-buffered: R fills one while T drains the other)
+enum { WF2_Q_T = 0, WF2_Q_A = 1, WF2_Q_B = 2, WF2_Q_R = 3, WF2_Q_F0 = 4, WF2_Q_F1 = 5 };
 #define WF2_MASK (TB_WF2_PATHS - 1)
 #define WF2_LOG2_PATHS (TB_WF2_PATHS == 1024 ? 10 : TB_WF2_PATHS == 512 ? 9 : TB_WF2_PATHS == 256 ? 8 : 7)
 
@@ -277,11 +280,15 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
         S.ring[WF2_Q_T][s] = 0;
         S.ring[WF2_Q_A][s] = 0;
         S.ring[WF2_Q_B][s] = 0;
+        S.ring[WF2_Q_F0][s] = 0;
+        S.ring[WF2_Q_F1][s] = 0;
         S.sample[s] = 0xffffffffu;
     }
     if (tid == 0) {
-        for (int q = 0; q < 4; ++q) S.head[q] = S.tail[q] = 0u;
+        for (int q = 0; q < 6; ++q) S.head[q] = S.tail[q] = 0u;
         S.tail[WF2_Q_R] = TB_WF2_PATHS;
+        S.snap[0] = TB_WF2_PATHS;
+        S.snap[1] = S.snap[2] = S.snap[3] = S.snap[4] = 0u;
         S.pref = WF2_Q_R;
         S.live = TB_WF2_PATHS;
         S.exhausted = 0;
@@ -293,8 +300,8 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
 
     // Two scheduling modes share the stage code below (P.hardPhases, uniform for the launch):
     //
-    //  * hard phases: all warps of the CTA work on the same stage, claiming chunks dynamically
-    //    until its queue is empty, then meet at a block barrier and move on (R -> T -> A -> B -> R).
+    //  * hard phases: all warps of the CTA work through the same short list of stages, claiming
+    //    chunks dynamically until each queue is empty, and meet at a block barrier twice per cycle.
     //    The kernel is far larger than the instruction cache, so warps that execute the same
     //    code at the same time share every instruction line; this is the faster mode when rays
     //    cost about the same (small scenes held in shared memory).
@@ -303,25 +310,55 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     //    (dragging the preference along).  Nobody ever waits for a slow ray, which wins when ray
     //    cost varies wildly (deep mesh BVHs) and the hot loop is small enough to stay cached.
     const bool hard = P.hardPhases != 0;
-    int phase = WF2_Q_R;
-    unsigned int phaseTail = TB_WF2_PATHS;   // every slot starts in the R queue
+    // hard-phase schedule: each cycle is two block-synchronous phases,
+    //   phase 0:  R (finished slots -> fresh camera rays into F[cycle&1]),  T,  F[~cycle&1]
+    //   phase 1:  A,  B
+    // Inside a phase the stages run back to back without a barrier: they consume queues that were
+    // completed before the phase began (so their tails are fixed and tickets cannot overshoot into
+    // missing entries) and touch disjoint slots.  step 0..4 = R, T, F, A, B.
+    int step = 0, cycle = 0;
+    unsigned int stepTail = TB_WF2_PATHS;   // every slot starts in the R queue
+    int stepQueue = WF2_Q_R;
 
     for (;;) {
         int s = 0, n = 0, stage = -1;
         if (hard) {
-            n = wf2_claim_ticket(S, phase, phaseTail, s);
+            n = wf2_claim_ticket(S, stepQueue, stepTail, s);
             if (n > 0) {
-                stage = phase;
+                stage = stepQueue;
             } else {
-                // this stage's queue is drained (nobody pushes into the stage being run).  After the
-                // barrier no warp holds or requests a ticket of this stage any more, so thread 0 can
-                // undo the overshoot of the failed requests (head back to tail) before the stage
-                // comes round again.
-                __syncthreads();
-                if (tid == 0) S.head[phase] = phaseTail;
-                if (phase == WF2_Q_R && *(volatile int*)&S.live <= 0) break;   // `live` only changes during R
-                phase = (phase + 1) & 3;
-                phaseTail = *(volatile unsigned int*)&S.tail[phase];   // stable until this stage ends
+                // this stage's queue is drained; at the end of a phase meet the other warps, undo the
+                // overshoot of the failed ticket requests (head back to the tail the stage ran with)
+                const bool endOfPhase = (step == 2 || step == 4);
+                if (endOfPhase) {
+                    __syncthreads();
+                    if (tid == 0) {
+                        if (step == 2) {
+                            S.head[WF2_Q_R] = S.snap[0];
+                            S.head[WF2_Q_T] = S.snap[1];
+                            S.head[WF2_Q_F0 + ((cycle + 1) & 1)] = S.snap[2];
+                        } else {
+                            S.head[WF2_Q_A] = S.snap[3];
+                            S.head[WF2_Q_B] = S.snap[4];
+                        }
+                    }
+                    if (step == 2 && *(volatile int*)&S.live <= 0) {
+                        // `live` only changes during R; nothing is left anywhere once it reaches zero
+                        break;
+                    }
+                }
+                if (step == 4) {
+                    step = 0;
+                    ++cycle;
+                } else {
+                    ++step;
+                }
+                stepQueue = step == 0 ? WF2_Q_R : step == 1 ? WF2_Q_T : step == 2 ? WF2_Q_F0 + ((cycle + 1) & 1)
+                          : step == 3 ? WF2_Q_A : WF2_Q_B;
+                // the queue was completed before this phase began; thread 0 publishes the tail every
+                // warp of the CTA uses (and that the head is reset to afterwards)
+                stepTail = *(volatile unsigned int*)&S.tail[stepQueue];
+                if (tid == 0) S.snap[step] = stepTail;
                 continue;
             }
         } else {
@@ -399,11 +436,11 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                 }
             }
             __threadfence_block();
-            wf2_push(S, WF2_Q_T, fresh, s);
+            wf2_push(S, hard ? WF2_Q_F0 + (cycle & 1) : WF2_Q_T, fresh, s);
             // slots that could not be refilled die: the CTA exits when none is left
             const unsigned dead = __ballot_sync(0xffffffffu, active && !fresh);
             if (dead && lane == 0) atomicSub(&S.live, __popc(dead));
-        } else if (stage == WF2_Q_T) {
+        } else if (stage == WF2_Q_T || stage >= WF2_Q_F0) {
             // ===================== T: trace the pending ray =======================================
             bool isExt = false, isNee = false;
             if (active) {
