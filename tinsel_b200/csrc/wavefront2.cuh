@@ -72,10 +72,11 @@ struct Wf2Shared {
     float sumx[TB_WF2_PATHS], sumy[TB_WF2_PATHS], sumz[TB_WF2_PATHS];
     float lax[TB_WF2_PATHS], lay[TB_WF2_PATHS], laz[TB_WF2_PATHS];
     uint32_t cursor[TB_WF2_PATHS];    // slot | prim << 8 | sample << 20
+    uint32_t tmask[TB_WF2_PATHS];     // pending mesh instances of the ray being traced | tie << 16
     // stage queues: rings of lap-tagged slot ids
-    uint16_t ring[6][TB_WF2_PATHS];
-    unsigned int head[6], tail[6];
-    unsigned int snap[5];             // hard-phase mode: the tail each stage of the current phase runs with
+    uint16_t ring[8][TB_WF2_PATHS];
+    unsigned int head[8], tail[8];
+    unsigned int snap[6];             // hard-phase mode: the tail each stage of the current phase runs with
     int pref;                         // stage the warps currently prefer (soft phases, see the main loop)
     int live;                         // slots that still hold (or may still receive) a path
     int exhausted;
@@ -85,9 +86,10 @@ struct Wf2Shared {
     ProgOp flat[32];
 };
 
-// stage queues.  T, A, B, R in the cyclic order of the free-running sweep; F0/F1 hold the freshly
-// regenerated camera rays in hard-phase mode (double-buffered: R fills one while T drains the other)
-enum { WF2_Q_T = 0, WF2_Q_A = 1, WF2_Q_B = 2, WF2_Q_R = 3, WF2_Q_F0 = 4, WF2_Q_F1 = 5 };
+// stage queues.  T, M, A, B, R in the cyclic order of the free-running sweep.  In hard-phase mode
+// the queues whose producer and consumer run in the same phase are double-buffered by cycle parity:
+// F0/F1 (fresh camera rays, R -> T) and M0/M1 (rays that still need mesh traversal, T -> M).
+enum { WF2_Q_T = 0, WF2_Q_M0 = 1, WF2_Q_A = 2, WF2_Q_B = 3, WF2_Q_R = 4, WF2_Q_F0 = 5, WF2_Q_F1 = 6, WF2_Q_M1 = 7 };
 #define WF2_MASK (TB_WF2_PATHS - 1)
 #define WF2_LOG2_PATHS (TB_WF2_PATHS == 1024 ? 10 : TB_WF2_PATHS == 512 ? 9 : TB_WF2_PATHS == 256 ? 8 : 7)
 
@@ -282,13 +284,15 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
         S.ring[WF2_Q_B][s] = 0;
         S.ring[WF2_Q_F0][s] = 0;
         S.ring[WF2_Q_F1][s] = 0;
+        S.ring[WF2_Q_M0][s] = 0;
+        S.ring[WF2_Q_M1][s] = 0;
         S.sample[s] = 0xffffffffu;
     }
     if (tid == 0) {
-        for (int q = 0; q < 6; ++q) S.head[q] = S.tail[q] = 0u;
+        for (int q = 0; q < 8; ++q) S.head[q] = S.tail[q] = 0u;
         S.tail[WF2_Q_R] = TB_WF2_PATHS;
         S.snap[0] = TB_WF2_PATHS;
-        S.snap[1] = S.snap[2] = S.snap[3] = S.snap[4] = 0u;
+        S.snap[1] = S.snap[2] = S.snap[3] = S.snap[4] = S.snap[5] = 0u;
         S.pref = WF2_Q_R;
         S.live = TB_WF2_PATHS;
         S.exhausted = 0;
@@ -311,11 +315,12 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     //    cost varies wildly (deep mesh BVHs) and the hot loop is small enough to stay cached.
     const bool hard = P.hardPhases != 0;
     // hard-phase schedule: each cycle is two block-synchronous phases,
-    //   phase 0:  R (finished slots -> fresh camera rays into F[cycle&1]),  T,  F[~cycle&1]
+    //   phase 0:  R (finished slots -> fresh camera rays into F[cycle&1]),  T (-> A, B, or M[cycle&1]
+    //             for rays that enter a mesh box),  F[~cycle&1],  M[~cycle&1] (-> A, B)
     //   phase 1:  A,  B
     // Inside a phase the stages run back to back without a barrier: they consume queues that were
     // completed before the phase began (so their tails are fixed and tickets cannot overshoot into
-    // missing entries) and touch disjoint slots.  step 0..4 = R, T, F, A, B.
+    // missing entries) and touch disjoint slots.  step 0..5 = R, T, F, M, A, B.
     int step = 0, cycle = 0;
     unsigned int stepTail = TB_WF2_PATHS;   // every slot starts in the R queue
     int stepQueue = WF2_Q_R;
@@ -329,32 +334,35 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
             } else {
                 // this stage's queue is drained; at the end of a phase meet the other warps, undo the
                 // overshoot of the failed ticket requests (head back to the tail the stage ran with)
-                const bool endOfPhase = (step == 2 || step == 4);
+                const bool endOfPhase = (step == 3 || step == 5);
                 if (endOfPhase) {
                     __syncthreads();
                     if (tid == 0) {
-                        if (step == 2) {
+                        if (step == 3) {
                             S.head[WF2_Q_R] = S.snap[0];
                             S.head[WF2_Q_T] = S.snap[1];
-                            S.head[WF2_Q_F0 + ((cycle + 1) & 1)] = S.snap[2];
+                            S.head[(cycle & 1) ? WF2_Q_F0 : WF2_Q_F1] = S.snap[2];
+                            S.head[(cycle & 1) ? WF2_Q_M0 : WF2_Q_M1] = S.snap[3];
                         } else {
-                            S.head[WF2_Q_A] = S.snap[3];
-                            S.head[WF2_Q_B] = S.snap[4];
+                            S.head[WF2_Q_A] = S.snap[4];
+                            S.head[WF2_Q_B] = S.snap[5];
                         }
                     }
-                    if (step == 2 && *(volatile int*)&S.live <= 0) {
+                    if (step == 3 && *(volatile int*)&S.live <= 0) {
                         // `live` only changes during R; nothing is left anywhere once it reaches zero
                         break;
                     }
                 }
-                if (step == 4) {
+                if (step == 5) {
                     step = 0;
                     ++cycle;
                 } else {
                     ++step;
                 }
-                stepQueue = step == 0 ? WF2_Q_R : step == 1 ? WF2_Q_T : step == 2 ? WF2_Q_F0 + ((cycle + 1) & 1)
-                          : step == 3 ? WF2_Q_A : WF2_Q_B;
+                stepQueue = step == 0 ? WF2_Q_R : step == 1 ? WF2_Q_T
+                          : step == 2 ? ((cycle & 1) ? WF2_Q_F0 : WF2_Q_F1)
+                          : step == 3 ? ((cycle & 1) ? WF2_Q_M0 : WF2_Q_M1)
+                          : step == 4 ? WF2_Q_A : WF2_Q_B;
                 // the queue was completed before this phase began; thread 0 publishes the tail every
                 // warp of the CTA uses (and that the head is reset to afterwards)
                 stepTail = *(volatile unsigned int*)&S.tail[stepQueue];
@@ -365,10 +373,10 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
             int p = 0;
             if (lane == 0) p = *(volatile int*)&S.pref;
             p = __shfl_sync(0xffffffffu, p, 0);
-            for (int k = 0; k < 8 && stage < 0; ++k) {
-                // k = 0..3: full chunks only; k = 4..7: whatever is left
-                const int q = (p + k) & 3;
-                n = wf2_claim(S, q, k < 4 ? 32 : 1, s);
+            for (int k = 0; k < 10 && stage < 0; ++k) {
+                // k = 0..4: full chunks only; k = 5..9: whatever is left
+                const int q = (p + k) % 5;
+                n = wf2_claim(S, q, k < 5 ? 32 : 1, s);
                 if (n > 0) stage = q;
             }
             if (stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
@@ -436,13 +444,17 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                 }
             }
             __threadfence_block();
-            wf2_push(S, hard ? WF2_Q_F0 + (cycle & 1) : WF2_Q_T, fresh, s);
+            wf2_push(S, hard ? ((cycle & 1) ? WF2_Q_F1 : WF2_Q_F0) : WF2_Q_T, fresh, s);
             // slots that could not be refilled die: the CTA exits when none is left
             const unsigned dead = __ballot_sync(0xffffffffu, active && !fresh);
             if (dead && lane == 0) atomicSub(&S.live, __popc(dead));
-        } else if (stage == WF2_Q_T || stage >= WF2_Q_F0) {
-            // ===================== T: trace the pending ray =======================================
-            bool isExt = false, isNee = false;
+        } else if (stage != WF2_Q_A && stage != WF2_Q_B) {
+            // ===================== T / M: trace the pending ray ===================================
+            // T runs the scene program (planes, spheres, box tests); rays that enter the box of a
+            // mesh instance continue in M, which traverses the mesh BVHs -- the long, divergent part
+            // of a trace -- on chunks made only of such rays.
+            const bool meshStage = (stage == WF2_Q_M0 || stage == WF2_Q_M1);
+            bool isExt = false, isNee = false, toMesh = false;
             if (active) {
                 const uint32_t fl = S.flags[s];
                 V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
@@ -458,21 +470,47 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                     o = p + face_forward(nn, d) * TB_RAY_EPS;
                 }
                 if (isNee || maxDepth > 0) {
-                    // one traversal instance serves both ray kinds (normals only for extension rays)
-                    const Hit h = trace_closest(sc, o, d, time, isExt);
-                    if (isExt) {
-                        S.ht[s] = h.t;
-                        S.hnx[s] = h.n.x; S.hny[s] = h.n.y; S.hnz[s] = h.n.z;
-                        S.hprim[s] = h.prim;
+                    TracePartial tp;
+                    if (meshStage) {
+                        const uint32_t tm = S.tmask[s];
+                        tp.minT = isExt ? S.ht[s] : S.st[s];
+                        tp.closest = isExt ? S.hprim[s] : S.sprim[s];
+                        tp.meshMask = tm & 0xffffu;
+                        tp.tie = ((tm >> 16) & 1u) != 0u;
+                        tp.ordered = false;
                     } else {
-                        S.st[s] = h.t;
-                        S.sprim[s] = h.prim;
+                        trace_program(sc, o, d, time, tp);
+                        toMesh = tp.meshMask != 0u && !tp.ordered;
+                    }
+                    if (toMesh) {
+                        // park the partial result in the record the final hit will overwrite (an
+                        // extension ray's old hit record is dead; a shadow ray has its own fields)
+                        if (isExt) {
+                            S.ht[s] = tp.minT;
+                            S.hprim[s] = tp.closest;
+                        } else {
+                            S.st[s] = tp.minT;
+                            S.sprim[s] = tp.closest;
+                        }
+                        S.tmask[s] = tp.meshMask | (tp.tie ? 1u << 16 : 0u);
+                        isExt = isNee = false;
+                    } else {
+                        const Hit h = trace_finish(sc, o, d, time, isExt, tp);
+                        if (isExt) {
+                            S.ht[s] = h.t;
+                            S.hnx[s] = h.n.x; S.hny[s] = h.n.y; S.hnz[s] = h.n.z;
+                            S.hprim[s] = h.prim;
+                        } else {
+                            S.st[s] = h.t;
+                            S.sprim[s] = h.prim;
+                        }
                     }
                 } else {
                     S.hprim[s] = -2;   // maxDepth == 0: no trace at all, radiance stays 0
                 }
             }
             __threadfence_block();
+            wf2_push(S, hard ? ((cycle & 1) ? WF2_Q_M1 : WF2_Q_M0) : WF2_Q_M0, toMesh, s);
             wf2_push(S, WF2_Q_A, isExt, s);
             wf2_push(S, WF2_Q_B, isNee, s);
         } else if (stage == WF2_Q_A) {
