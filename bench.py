@@ -291,7 +291,7 @@ def run_ours(args):
     if rank == 0:
         algo = load_algo_bytes()
         peak, peak_src = read_peaks()
-        # dominant kernel: k_wavefront (one launch per step per rank); its share of the step is ~100 %
+        # dominant kernel: k_wavefront2 (one launch per step per rank); its share of the step is ~100 %
         per_launch_samples = WIDTH * HEIGHT * SPP_PER_STEP / world
         avg_launch_s = (sum(step_ms) / len(step_ms)) / 1e3
         achieved = algo["bytes_per_sample"] * per_launch_samples / avg_launch_s / 1e9
@@ -311,7 +311,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": algo.get("dram_traffic_bytes_per_launch"),
-                         "kernel": "k_wavefront", "peak_source": peak_src,
+                         "kernel": "k_wavefront2", "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": algo["bytes_per_sample"],
                          "note": "algorithmic bytes on the reference traversal order; the working set is SMEM/L2 resident so DRAM traffic is far below it"},
             "cpu_baseline": {"value": cpu_msps, "unit": "Msamples/s", "cores": cores, "kind": kind,

@@ -70,6 +70,7 @@ struct DPrim {
     int mesh;
     int lightSamples;
     float area;           // PrimitiveArea, intersection.h:833-853
+    int deferMesh;        // mesh big enough for its traversal to run in the wavefront's mesh stage
     DMaterial mat;
 };
 
@@ -402,6 +403,7 @@ struct TracePartial {
     uint32_t meshMask;    // bit i: primitive i is a mesh instance that must be traversed
     bool tie;             // two primitives returned exactly the same t: redo in reference order
     bool ordered;         // the flat program cannot be used for this ray: use trace_ordered()
+    PrimHit best;         // triangle record when `closest` is a small mesh traversed inline
 };
 
 TB_DEV void trace_program(const DScene& sc, V3 o, V3 d, float time, TracePartial& tp)
@@ -413,6 +415,7 @@ TB_DEV void trace_program(const DScene& sc, V3 o, V3 d, float time, TracePartial
     tp.closest = -1;
     tp.meshMask = 0u;
     tp.tie = false;
+    tp.best.t = 0.0f; tp.best.tri = 0; tp.best.u = tp.best.v = tp.best.w = 0.0f; tp.best.gn = v3s(0.0f);
     tp.ordered = (n == 0 || !guard);
     if (tp.ordered) return;
 
@@ -445,13 +448,14 @@ TB_DEV void trace_program(const DScene& sc, V3 o, V3 d, float time, TracePartial
                 }
             }
             const DPrim& p = sc.prims[kindPrim >> 8];
-            if (p.type == TB200_MESH) {
+            if (p.type == TB200_MESH && p.deferMesh) {
                 tp.meshMask |= 1u << (kindPrim >> 8);
                 continue;
             }
             PrimHit ph;
-            if (!prim_test(sc, p, o, d, time, ph)) continue;   // sphere (or a transformed plane)
+            if (!prim_test(sc, p, o, d, time, ph)) continue;   // sphere, small mesh (or a transformed plane)
             t = ph.t;
+            if (p.type == TB200_MESH && t > 0.0f && t < tp.minT) tp.best = ph;
         }
         if (t > 0.0f) {
             if (t < tp.minT) {
@@ -471,8 +475,7 @@ TB_DEV Hit trace_finish(const DScene& sc, V3 o, V3 d, float time, bool wantNorma
     float minT = tp.minT;
     int closest = tp.closest;
     bool tie = tp.tie;
-    PrimHit best;
-    best.t = minT; best.tri = 0; best.u = best.v = best.w = 0.0f; best.gn = v3s(0.0f);
+    PrimHit best = tp.best;
     uint32_t mask = tp.meshMask;
     while (mask) {
         const int index = __ffs(mask) - 1;
