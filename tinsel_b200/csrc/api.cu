@@ -394,8 +394,6 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
             d.area = s->meshes[p.mesh].area * p.end.s;
         else
             d.area = 0.0f;
-        // meshes beyond a handful of triangles are traversed in the wavefront's mesh stage
-        d.deferMesh = (p.type == TB200_MESH && p.mesh >= 0 && p.mesh < s->numMeshes && s->meshes[p.mesh].numIndices / 3 > 64) ? 1 : 0;
         d.mat = make_material(p.material);
         if (p.type == TB200_MESH && (p.mesh < 0 || p.mesh >= s->numMeshes)) return set_error("primitive references a missing mesh");
         if (p.lightSamples > 0) numNee += p.lightSamples;

@@ -70,7 +70,6 @@ struct DPrim {
     int mesh;
     int lightSamples;
     float area;           // PrimitiveArea, intersection.h:833-853
-    int deferMesh;        // mesh big enough for its traversal to run in the wavefront's mesh stage
     DMaterial mat;
 };
 
@@ -168,10 +167,7 @@ struct MeshHit {
     V3 n;   // closestNormal = n*sign, unnormalised (intersection.h:658)
 };
 
-// IntersectRayMesh + MeshQuery, intersection.h:629-749.  Same visit order, culling and tie-breaks as
-// the reference's `while(count)` loop, arranged as "while-while" (interior nodes are descended in an
-// inner loop, leaves handled outside it) so that the lanes of a warp spend fewer iterations on
-// mixed node kinds, and with the next node kept in a register instead of a push followed by a pop.
+// IntersectRayMesh + MeshQuery, intersection.h:629-749
 static __device__ __noinline__ bool ray_mesh(const DMesh& m, V3 origin, V3 dir, MeshHit& out)
 {
     V3 rcp;
@@ -180,42 +176,16 @@ static __device__ __noinline__ bool ray_mesh(const DMesh& m, V3 origin, V3 dir, 
     rcp.z = 1.0f / dir.z;
 
     uint32_t stack[TB_STACK];
-    int count = 0;
-    uint32_t ref = m.rootRef;
-    bool live = true;
+    stack[0] = m.rootRef;
+    int count = 1;
 
     float closestT = FLT_MAX;
     float tmax = FLT_MAX;
     out.tri = -1;
 
-    while (live) {
-        while (live && !(ref & TB_LEAF)) {
-            const BvhPair* pr = &m.pairs[ref];
-            const float4 a = __ldg(&pr->a), b = __ldg(&pr->b), c = __ldg(&pr->c);
-            const uint2 kids = __ldg(reinterpret_cast<const uint2*>(&pr->left));
-            float tLeft, tRight;
-            const bool hitLeft = ray_aabb(origin, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft) && tLeft < tmax;
-            const bool hitRight = ray_aabb(origin, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight) && tRight < tmax;
-            uint32_t left = kids.x, right = kids.y;
-            // "traverse closest first": only the indices swap, not the hit flags (intersection.h:716-727)
-            if (hitLeft && hitRight && (tLeft < tRight)) {
-                const uint32_t tmp = left;
-                left = right;
-                right = tmp;
-            }
-            // reference: push left (if hitLeft), push right (if hitRight), pop -> the last one pushed
-            if (hitRight) {
-                if (hitLeft) stack[count++] = left;
-                ref = right;
-            } else if (hitLeft) {
-                ref = left;
-            } else if (count) {
-                ref = stack[--count];
-            } else {
-                live = false;
-            }
-        }
-        if (live) {
+    while (count) {
+        const uint32_t ref = stack[--count];
+        if (ref & TB_LEAF) {
             const uint32_t i = ref & ~TB_LEAF;
             const float4 q0 = __ldg(&m.triVerts[i * 3 + 0]);
             const float4 q1 = __ldg(&m.triVerts[i * 3 + 1]);
@@ -233,8 +203,22 @@ static __device__ __noinline__ bool ray_mesh(const DMesh& m, V3 origin, V3 dir, 
                 }
             }
             tmax = closestT;  // "truncate ray", intersection.h:700
-            if (count) ref = stack[--count];
-            else live = false;
+        } else {
+            const BvhPair* pr = &m.pairs[ref];
+            const float4 a = __ldg(&pr->a), b = __ldg(&pr->b), c = __ldg(&pr->c);
+            const uint2 kids = __ldg(reinterpret_cast<const uint2*>(&pr->left));
+            float tLeft, tRight;
+            const bool hitLeft = ray_aabb(origin, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft) && tLeft < tmax;
+            const bool hitRight = ray_aabb(origin, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight) && tRight < tmax;
+            uint32_t left = kids.x, right = kids.y;
+            // "traverse closest first": only the indices swap, not the hit flags (intersection.h:716-727)
+            if (hitLeft && hitRight && (tLeft < tRight)) {
+                const uint32_t tmp = left;
+                left = right;
+                right = tmp;
+            }
+            if (hitLeft) stack[count++] = left;
+            if (hitRight) stack[count++] = right;
         }
     }
     if (closestT < FLT_MAX) {
@@ -394,35 +378,27 @@ struct __align__(16) ProgOp {
     int bits;        // guard bit (TB_BIT_ALWAYS: unconditional) | own bit << 8 (BOX only)
 };
 
-// Result of the first half of a trace: closest hit among the non-mesh primitives plus the set of
-// mesh instances whose (finite) boxes the ray enters.  Mesh traversal is the expensive, divergent
-// part of a trace; the wavefront kernel runs it as a stage of its own on exactly these rays.
-struct TracePartial {
-    float minT;
-    int closest;          // primitive index of the closest non-mesh hit so far, -1 if none
-    uint32_t meshMask;    // bit i: primitive i is a mesh instance that must be traversed
-    bool tie;             // two primitives returned exactly the same t: redo in reference order
-    bool ordered;         // the flat program cannot be used for this ray: use trace_ordered()
-    PrimHit best;         // triangle record when `closest` is a small mesh traversed inline
-};
-
-TB_DEV void trace_program(const DScene& sc, V3 o, V3 d, float time, TracePartial& tp)
+TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNormal)
 {
     const int n = sc.numFlat;
     const bool guard = (fabsf(o.x) < 1.0e7f) & (fabsf(o.y) < 1.0e7f) & (fabsf(o.z) < 1.0e7f) & (d.x == d.x) & (d.y == d.y) &
                        (d.z == d.z);
-    tp.minT = FLT_MAX;
-    tp.closest = -1;
-    tp.meshMask = 0u;
-    tp.tie = false;
-    tp.best.t = 0.0f; tp.best.tri = 0; tp.best.u = tp.best.v = tp.best.w = 0.0f; tp.best.gn = v3s(0.0f);
-    tp.ordered = (n == 0 || !guard);
-    if (tp.ordered) return;
+    if (n == 0 || !guard) return trace_ordered(sc, o, d, time, wantNormal);
 
     V3 rcp;
     rcp.x = 1.0f / d.x;
     rcp.y = 1.0f / d.y;
     rcp.z = 1.0f / d.z;
+
+    float minT = FLT_MAX;
+    int closest = -1;
+    bool tie = false;
+    // triangle record of the closest mesh hit.  Kept in (local) memory behind a run-time index on
+    // purpose: as a register struct it is copied around on every iteration of the op loop, planes
+    // included, which costs more than the whole plane test.
+    PrimHit rec[2];
+    int ri = 0;
+    rec[0].t = 0.0f; rec[0].tri = 0; rec[0].u = rec[0].v = rec[0].w = 0.0f; rec[0].gn = v3s(0.0f);
     uint32_t visited = 0u;
 
     for (int i = 0; i < n; ++i) {
@@ -447,49 +423,17 @@ TB_DEV void trace_program(const DScene& sc, V3 o, V3 d, float time, TracePartial
                     continue;
                 }
             }
-            const DPrim& p = sc.prims[kindPrim >> 8];
-            if (p.type == TB200_MESH && p.deferMesh) {
-                tp.meshMask |= 1u << (kindPrim >> 8);
-                continue;
-            }
-            PrimHit ph;
-            if (!prim_test(sc, p, o, d, time, ph)) continue;   // sphere, small mesh (or a transformed plane)
-            t = ph.t;
-            if (p.type == TB200_MESH && t > 0.0f && t < tp.minT) tp.best = ph;
+            PrimHit* ph = &rec[ri ^ 1];
+            if (!prim_test(sc, sc.prims[kindPrim >> 8], o, d, time, *ph)) continue;
+            t = ph->t;
+            if (t > 0.0f && t < minT) ri ^= 1;   // the record just written becomes the best one
         }
         if (t > 0.0f) {
-            if (t < tp.minT) {
-                tp.minT = t;
-                tp.closest = kindPrim >> 8;
-            } else if (t == tp.minT) {
-                tp.tie = true;
-            }
-        }
-    }
-}
-
-// Second half: traverse the recorded mesh instances, settle ties, produce the normal.
-TB_DEV Hit trace_finish(const DScene& sc, V3 o, V3 d, float time, bool wantNormal, const TracePartial& tp)
-{
-    if (tp.ordered) return trace_ordered(sc, o, d, time, wantNormal);
-    float minT = tp.minT;
-    int closest = tp.closest;
-    bool tie = tp.tie;
-    PrimHit best = tp.best;
-    uint32_t mask = tp.meshMask;
-    while (mask) {
-        const int index = __ffs(mask) - 1;
-        mask &= mask - 1u;
-        PrimHit ph;
-        if (prim_test(sc, sc.prims[index], o, d, time, ph)) {
-            if (ph.t > 0.0f) {
-                if (ph.t < minT) {
-                    minT = ph.t;
-                    closest = index;
-                    best = ph;
-                } else if (ph.t == minT) {
-                    tie = true;
-                }
+            if (t < minT) {
+                minT = t;
+                closest = kindPrim >> 8;
+            } else if (t == minT) {
+                tie = true;
             }
         }
     }
@@ -499,16 +443,9 @@ TB_DEV Hit trace_finish(const DScene& sc, V3 o, V3 d, float time, bool wantNorma
     h.prim = closest;
     V3 nrm = v3s(0.0f);
     if (wantNormal && closest >= 0) {
-        best.t = minT;   // spheres recompute their normal from t (prim_normal)
-        nrm = prim_normal(sc, sc.prims[closest], o, d, time, best);
+        rec[ri].t = minT;
+        nrm = prim_normal(sc, sc.prims[closest], o, d, time, rec[ri]);
     }
     h.n = face_forward(nrm, -d);
     return h;
-}
-
-TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNormal)
-{
-    TracePartial tp;
-    trace_program(sc, o, d, time, tp);
-    return trace_finish(sc, o, d, time, wantNormal, tp);
 }

@@ -72,11 +72,10 @@ struct Wf2Shared {
     float sumx[TB_WF2_PATHS], sumy[TB_WF2_PATHS], sumz[TB_WF2_PATHS];
     float lax[TB_WF2_PATHS], lay[TB_WF2_PATHS], laz[TB_WF2_PATHS];
     uint32_t cursor[TB_WF2_PATHS];    // slot | prim << 8 | sample << 20
-    uint32_t tmask[TB_WF2_PATHS];     // pending mesh instances of the ray being traced | tie << 16
     // stage queues: rings of lap-tagged slot ids
-    uint16_t ring[8][TB_WF2_PATHS];
-    unsigned int head[8], tail[8];
-    unsigned int snap[6];             // hard-phase mode: the tail each stage of the current phase runs with
+    uint16_t ring[6][TB_WF2_PATHS];
+    unsigned int head[6], tail[6];
+    unsigned int snap[5];             // hard-phase mode: the tail each stage of the current phase runs with
     int pref;                         // stage the warps currently prefer (soft phases, see the main loop)
     int live;                         // slots that still hold (or may still receive) a path
     int exhausted;
@@ -86,10 +85,9 @@ struct Wf2Shared {
     ProgOp flat[32];
 };
 
-// stage queues.  T, M, A, B, R in the cyclic order of the free-running sweep.  In hard-phase mode
-// the queues whose producer and consumer run in the same phase are double-buffered by cycle parity:
-// F0/F1 (fresh camera rays, R -> T) and M0/M1 (rays that still need mesh traversal, T -> M).
-enum { WF2_Q_T = 0, WF2_Q_M0 = 1, WF2_Q_A = 2, WF2_Q_B = 3, WF2_Q_R = 4, WF2_Q_F0 = 5, WF2_Q_F1 = 6, WF2_Q_M1 = 7 };
+// stage queues.  T, A, B, R in the cyclic order of the free-running sweep; F0/F1 hold the freshly
+// regenerated camera rays in hard-phase mode (double-buffered: R fills one while T drains the other)
+enum { WF2_Q_T = 0, WF2_Q_A = 1, WF2_Q_B = 2, WF2_Q_R = 3, WF2_Q_F0 = 4, WF2_Q_F1 = 5 };
 #define WF2_MASK (TB_WF2_PATHS - 1)
 #define WF2_LOG2_PATHS (TB_WF2_PATHS == 1024 ? 10 : TB_WF2_PATHS == 512 ? 9 : TB_WF2_PATHS == 256 ? 8 : 7)
 
@@ -121,7 +119,7 @@ TB_DEV void wf2_push(Wf2Shared& S, int q, bool flag, int slot)
 // Claim up to 32 entries of queue q for this warp.  Returns the number claimed (warp-uniform);
 // lane i < n receives its slot.  Lock-free: cells are read first, ownership is taken with a CAS
 // on head, so a stalled warp can never read a cell that a producer has already recycled.
-TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot, int maxCount = 32)
+TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot)
 {
     const int lane = threadIdx.x & 31;
     int notReady = 0;
@@ -135,7 +133,7 @@ TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot, int maxCount 
         t = __shfl_sync(0xffffffffu, t, 0);
         int n = (int)(t - h);
         if (n < minCount) return 0;
-        if (n > maxCount) n = maxCount;
+        if (n > 32) n = 32;
         // optimistic read; entries reserved by a producer but not yet stored end the chunk early
         const unsigned int idx = h + (unsigned)lane;
         const uint16_t cell = *(volatile uint16_t*)&S.ring[q][idx & WF2_MASK];
@@ -161,31 +159,17 @@ TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot, int maxCount 
 // Hard-phase variant: while a stage runs nobody pushes into its queue, so `tail` is fixed and a
 // ticket (atomicAdd on head) can never overshoot into entries that do not exist yet.  `head` is
 // put back to `tail` by thread 0 after the barrier that ends the stage.
-TB_DEV int wf2_claim_ticket(Wf2Shared& S, int q, unsigned int tail, int& slot, int maxCount = 32)
+TB_DEV int wf2_claim_ticket(Wf2Shared& S, int q, unsigned int tail, int& slot)
 {
     const int lane = threadIdx.x & 31;
     unsigned int base = 0;
-    if (lane == 0) base = atomicAdd(&S.head[q], (unsigned)maxCount);
+    if (lane == 0) base = atomicAdd(&S.head[q], 32u);
     base = __shfl_sync(0xffffffffu, base, 0);
     const int avail = (int)(tail - base);
     if (avail <= 0) return 0;
-    const int n = avail < maxCount ? avail : maxCount;
+    const int n = avail < 32 ? avail : 32;
     if (lane < n) slot = (int)(*(volatile uint16_t*)&S.ring[q][(base + (unsigned)lane) & WF2_MASK] & 1023u);
     return n;
-}
-
-// the ray a slot is waiting on: its extension ray, or (NEE phase) the shadow ray from the surface
-// point, origin = p + FaceForward(n, wi)*eps (render.cpp:121,170)
-TB_DEV void wf2_pending_ray(const Wf2Shared& S, int s, bool isExt, V3& o, V3& d)
-{
-    o = v3(S.ox[s], S.oy[s], S.oz[s]);
-    d = v3(S.dx[s], S.dy[s], S.dz[s]);
-    if (!isExt) {
-        const V3 p = o + d * S.ht[s];
-        const V3 nn = v3(S.hnx[s], S.hny[s], S.hnz[s]);
-        d = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
-        o = p + face_forward(nn, d) * TB_RAY_EPS;
-    }
 }
 
 TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s)
@@ -260,209 +244,6 @@ TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf
     return true;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Stage M: mesh BVH traversal with per-lane refill.  Visit counts differ by two orders of magnitude
-// between rays (a ray that misses the root's children vs one that grazes the surface), so a chunk of
-// 32 rays traversed in lock step ends up on ~5 live lanes.  Here every lane owns one (ray, mesh) job
-// at a time; after every TB_WF2_MESH_STEPS node visits the warp hands finished lanes their result
-// (merge, normal, hit record, push to A/B) and refills idle lanes from the M queue, so the node loop
-// stays populated until the queue runs dry.  The walk itself is ray_mesh()'s: child-pair records,
-// near child first, `tLeft < tmax` culling, first-found-wins on equal t -- the reference's order.
-// ---------------------------------------------------------------------------------------------------
-#ifndef TB_WF2_MESH_STEPS
-#define TB_WF2_MESH_STEPS 16
-#endif
-
-static __device__ __noinline__ void wf2_mesh_stage(Wf2Shared& S, const DScene& sc, int q, bool hard, unsigned int ticketTail)
-{
-    const int lane = threadIdx.x & 31;
-    // per-lane job state
-    bool busy = false;
-    int slot = 0;
-    bool isExt = false;
-    uint32_t mask = 0u;          // mesh instances still to traverse for this ray
-    float minT = FLT_MAX;        // scene-level closest so far
-    int closest = -1;
-    bool tie = false;
-    PrimHit best;
-    best.t = 0.0f; best.tri = 0; best.u = best.v = best.w = 0.0f; best.gn = v3s(0.0f);
-    // current mesh walk
-    int curPrim = -1;
-    const DMesh* mesh = nullptr;
-    V3 lo = v3s(0.0f), ld = v3s(0.0f), rcp = v3s(0.0f);
-    uint32_t stack[TB_STACK];
-    int count = 0;
-    uint32_t ref = 0u;
-    bool walking = false;
-    float closestT = FLT_MAX, tmax = FLT_MAX;
-    MeshHit cur;
-    cur.t = 0.0f; cur.u = cur.v = cur.w = 0.0f; cur.tri = -1; cur.n = v3s(0.0f);
-    bool drained = false;
-
-    for (;;) {
-        // ---- refill idle lanes ------------------------------------------------------------------
-        const unsigned idleMask = __ballot_sync(0xffffffffu, !busy);
-        const int idle = __popc(idleMask);
-        if (!drained && (idle == 32 || idle >= 8)) {
-            int claimed = 0;
-            const int n = hard ? wf2_claim_ticket(S, q, ticketTail, claimed, idle) : wf2_claim(S, q, 1, claimed, idle);
-            if (n == 0) drained = true;
-            const int rank = __popc(idleMask & ((1u << lane) - 1u));
-            const int mine = __shfl_sync(0xffffffffu, claimed, rank & 31);
-            if (!busy && rank < n) {
-                slot = mine;
-                busy = true;
-                const uint32_t fl = S.flags[slot];
-                isExt = ((fl >> 3) & 1u) == WF2_PH_EXT;
-                const uint32_t tm = S.tmask[slot];
-                mask = tm & 0xffffu;
-                tie = ((tm >> 16) & 1u) != 0u;
-                minT = isExt ? S.ht[slot] : S.st[slot];
-                closest = isExt ? S.hprim[slot] : S.sprim[slot];
-                walking = false;
-            }
-        }
-        if (__ballot_sync(0xffffffffu, busy) == 0u) break;   // nothing in flight, nothing left to claim
-
-        // ---- start the next mesh instance of the job ---------------------------------------------
-        if (busy && !walking && mask) {
-            curPrim = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            const DPrim& p = sc.prims[curPrim];
-            V3 o, d;
-            wf2_pending_ray(S, slot, isExt, o, d);
-            const Xf xf = prim_transform(p, S.time[slot]);
-            lo = inverse_transform_point(xf, o);      // PrimitiveIntersect, intersection.h:984-985
-            ld = inverse_transform_vector(xf, d);
-            rcp.x = 1.0f / ld.x;
-            rcp.y = 1.0f / ld.y;
-            rcp.z = 1.0f / ld.z;
-            mesh = &sc.meshes[p.mesh];
-            count = 0;
-            ref = mesh->rootRef;
-            closestT = FLT_MAX;
-            tmax = FLT_MAX;
-            cur.tri = -1;
-            walking = true;
-        }
-
-        // ---- walk: a bounded number of node visits per round ---------------------------------------
-        for (int step = 0; step < TB_WF2_MESH_STEPS; ++step) {
-            if (!__any_sync(0xffffffffu, busy && walking)) break;
-            if (busy && walking) {
-                if (!(ref & TB_LEAF)) {
-                    const BvhPair* pr = &mesh->pairs[ref];
-                    const float4 a = __ldg(&pr->a), b = __ldg(&pr->b), c = __ldg(&pr->c);
-                    const uint2 kids = __ldg(reinterpret_cast<const uint2*>(&pr->left));
-                    float tLeft, tRight;
-                    const bool hitLeft = ray_aabb(lo, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft) && tLeft < tmax;
-                    const bool hitRight = ray_aabb(lo, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight) && tRight < tmax;
-                    uint32_t left = kids.x, right = kids.y;
-                    if (hitLeft && hitRight && (tLeft < tRight)) {
-                        const uint32_t tmp = left;
-                        left = right;
-                        right = tmp;
-                    }
-                    if (hitRight) {
-                        if (hitLeft) stack[count++] = left;
-                        ref = right;
-                    } else if (hitLeft) {
-                        ref = left;
-                    } else if (count) {
-                        ref = stack[--count];
-                    } else {
-                        walking = false;
-                    }
-                } else {
-                    const uint32_t i = ref & ~TB_LEAF;
-                    const float4 q0 = __ldg(&mesh->triVerts[i * 3 + 0]);
-                    const float4 q1 = __ldg(&mesh->triVerts[i * 3 + 1]);
-                    const float4 q2 = __ldg(&mesh->triVerts[i * 3 + 2]);
-                    float t, u, v, w, sign;
-                    V3 nrm;
-                    if (ray_tri(lo, ld, v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), v3(q1.z, q1.w, q2.x), t, u, v, w, sign, nrm)) {
-                        if (t > 0.0f && t < closestT) {
-                            closestT = t;
-                            cur.u = u;
-                            cur.v = v;
-                            cur.w = w;
-                            cur.tri = (int)i;
-                            cur.n = nrm * sign;
-                        }
-                    }
-                    tmax = closestT;
-                    if (count) ref = stack[--count];
-                    else walking = false;
-                }
-            }
-        }
-
-        // ---- a mesh walk ended: merge into the scene-level closest hit (render.cpp:41-52) -----------
-        bool doneExt = false, doneNee = false;
-        if (busy && !walking) {
-            if (curPrim >= 0 && closestT < FLT_MAX) {
-                if (closestT > 0.0f) {
-                    if (closestT < minT) {
-                        minT = closestT;
-                        closest = curPrim;
-                        best.t = closestT;
-                        best.tri = cur.tri;
-                        best.u = cur.u;
-                        best.v = cur.v;
-                        best.w = cur.w;
-                        best.gn = cur.n;
-                    } else if (closestT == minT) {
-                        tie = true;
-                    }
-                }
-            }
-            curPrim = -1;
-            if (mask == 0u) {
-                // all instances done: settle ties, normal, hit record
-                V3 o, d;
-                wf2_pending_ray(S, slot, isExt, o, d);
-                const float time = S.time[slot];
-                Hit h;
-                if (tie) {
-                    h = trace_ordered(sc, o, d, time, isExt);
-                } else {
-                    h.t = minT;
-                    h.prim = closest;
-                    V3 nrm = v3s(0.0f);
-                    if (isExt && closest >= 0) {
-                        const DPrim& cp = sc.prims[closest];
-                        if (cp.type == TB200_MESH && !cp.deferMesh) {
-                            // the winner is a small mesh the T stage traversed inline: its triangle
-                            // record was not parked, so walk the (tiny) mesh again -- same result
-                            PrimHit ph;
-                            if (prim_test(sc, cp, o, d, time, ph)) best = ph;
-                        }
-                        best.t = minT;
-                        nrm = prim_normal(sc, cp, o, d, time, best);
-                    }
-                    h.n = face_forward(nrm, -d);
-                }
-                if (isExt) {
-                    S.ht[slot] = h.t;
-                    S.hnx[slot] = h.n.x; S.hny[slot] = h.n.y; S.hnz[slot] = h.n.z;
-                    S.hprim[slot] = h.prim;
-                    doneExt = true;
-                } else {
-                    S.st[slot] = h.t;
-                    S.sprim[slot] = h.prim;
-                    doneNee = true;
-                }
-                busy = false;
-            }
-        }
-        if (__any_sync(0xffffffffu, doneExt || doneNee)) {
-            __threadfence_block();
-            wf2_push(S, WF2_Q_A, doneExt, slot);
-            wf2_push(S, WF2_Q_B, doneNee, slot);
-        }
-    }
-}
-
 __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(LaunchParams P, unsigned long long total)
 {
     extern __shared__ __align__(16) unsigned char wf_smem_raw[];
@@ -501,15 +282,13 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
         S.ring[WF2_Q_B][s] = 0;
         S.ring[WF2_Q_F0][s] = 0;
         S.ring[WF2_Q_F1][s] = 0;
-        S.ring[WF2_Q_M0][s] = 0;
-        S.ring[WF2_Q_M1][s] = 0;
         S.sample[s] = 0xffffffffu;
     }
     if (tid == 0) {
-        for (int q = 0; q < 8; ++q) S.head[q] = S.tail[q] = 0u;
+        for (int q = 0; q < 6; ++q) S.head[q] = S.tail[q] = 0u;
         S.tail[WF2_Q_R] = TB_WF2_PATHS;
         S.snap[0] = TB_WF2_PATHS;
-        S.snap[1] = S.snap[2] = S.snap[3] = S.snap[4] = S.snap[5] = 0u;
+        S.snap[1] = S.snap[2] = S.snap[3] = S.snap[4] = 0u;
         S.pref = WF2_Q_R;
         S.live = TB_WF2_PATHS;
         S.exhausted = 0;
@@ -532,12 +311,11 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     //    cost varies wildly (deep mesh BVHs) and the hot loop is small enough to stay cached.
     const bool hard = P.hardPhases != 0;
     // hard-phase schedule: each cycle is two block-synchronous phases,
-    //   phase 0:  R (finished slots -> fresh camera rays into F[cycle&1]),  T (-> A, B, or M[cycle&1]
-    //             for rays that enter a mesh box),  F[~cycle&1],  M[~cycle&1] (-> A, B)
+    //   phase 0:  R (finished slots -> fresh camera rays into F[cycle&1]),  T,  F[~cycle&1]
     //   phase 1:  A,  B
     // Inside a phase the stages run back to back without a barrier: they consume queues that were
     // completed before the phase began (so their tails are fixed and tickets cannot overshoot into
-    // missing entries) and touch disjoint slots.  step 0..5 = R, T, F, M, A, B.
+    // missing entries) and touch disjoint slots.  step 0..4 = R, T, F, A, B.
     int step = 0, cycle = 0;
     unsigned int stepTail = TB_WF2_PATHS;   // every slot starts in the R queue
     int stepQueue = WF2_Q_R;
@@ -545,46 +323,38 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     for (;;) {
         int s = 0, n = 0, stage = -1;
         if (hard) {
-            if (step == 3) {
-                wf2_mesh_stage(S, sc, stepQueue, true, stepTail);   // claims its own entries until the queue is drained
-                n = 0;
-            } else {
-                n = wf2_claim_ticket(S, stepQueue, stepTail, s);
-            }
+            n = wf2_claim_ticket(S, stepQueue, stepTail, s);
             if (n > 0) {
                 stage = stepQueue;
             } else {
                 // this stage's queue is drained; at the end of a phase meet the other warps, undo the
                 // overshoot of the failed ticket requests (head back to the tail the stage ran with)
-                const bool endOfPhase = (step == 3 || step == 5);
+                const bool endOfPhase = (step == 2 || step == 4);
                 if (endOfPhase) {
                     __syncthreads();
                     if (tid == 0) {
-                        if (step == 3) {
+                        if (step == 2) {
                             S.head[WF2_Q_R] = S.snap[0];
                             S.head[WF2_Q_T] = S.snap[1];
-                            S.head[(cycle & 1) ? WF2_Q_F0 : WF2_Q_F1] = S.snap[2];
-                            S.head[(cycle & 1) ? WF2_Q_M0 : WF2_Q_M1] = S.snap[3];
+                            S.head[WF2_Q_F0 + ((cycle + 1) & 1)] = S.snap[2];
                         } else {
-                            S.head[WF2_Q_A] = S.snap[4];
-                            S.head[WF2_Q_B] = S.snap[5];
+                            S.head[WF2_Q_A] = S.snap[3];
+                            S.head[WF2_Q_B] = S.snap[4];
                         }
                     }
-                    if (step == 3 && *(volatile int*)&S.live <= 0) {
+                    if (step == 2 && *(volatile int*)&S.live <= 0) {
                         // `live` only changes during R; nothing is left anywhere once it reaches zero
                         break;
                     }
                 }
-                if (step == 5) {
+                if (step == 4) {
                     step = 0;
                     ++cycle;
                 } else {
                     ++step;
                 }
-                stepQueue = step == 0 ? WF2_Q_R : step == 1 ? WF2_Q_T
-                          : step == 2 ? ((cycle & 1) ? WF2_Q_F0 : WF2_Q_F1)
-                          : step == 3 ? ((cycle & 1) ? WF2_Q_M0 : WF2_Q_M1)
-                          : step == 4 ? WF2_Q_A : WF2_Q_B;
+                stepQueue = step == 0 ? WF2_Q_R : step == 1 ? WF2_Q_T : step == 2 ? WF2_Q_F0 + ((cycle + 1) & 1)
+                          : step == 3 ? WF2_Q_A : WF2_Q_B;
                 // the queue was completed before this phase began; thread 0 publishes the tail every
                 // warp of the CTA uses (and that the head is reset to afterwards)
                 stepTail = *(volatile unsigned int*)&S.tail[stepQueue];
@@ -595,24 +365,12 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
             int p = 0;
             if (lane == 0) p = *(volatile int*)&S.pref;
             p = __shfl_sync(0xffffffffu, p, 0);
-            for (int k = 0; k < 10 && stage == -1; ++k) {
-                // k = 0..4: full chunks only; k = 5..9: whatever is left
-                const int q = (p + k) % 5;
-                if (q == WF2_Q_M0) {
-                    unsigned int avail = 0;
-                    if (lane == 0) avail = *(volatile unsigned int*)&S.tail[q] - *(volatile unsigned int*)&S.head[q];
-                    avail = __shfl_sync(0xffffffffu, avail, 0);
-                    if ((int)avail >= (k < 5 ? 32 : 1)) {
-                        if (lane == 0 && p != q) *(volatile int*)&S.pref = q;
-                        wf2_mesh_stage(S, sc, q, false, 0u);
-                        stage = -2;   // did a whole stage; go round again
-                    }
-                    continue;
-                }
-                n = wf2_claim(S, q, k < 5 ? 32 : 1, s);
+            for (int k = 0; k < 8 && stage < 0; ++k) {
+                // k = 0..3: full chunks only; k = 4..7: whatever is left
+                const int q = (p + k) & 3;
+                n = wf2_claim(S, q, k < 4 ? 32 : 1, s);
                 if (n > 0) stage = q;
             }
-            if (stage == -2) continue;
             if (stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
             if (stage < 0) {
                 if (*(volatile int*)&S.live <= 0) break;
@@ -678,56 +436,43 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                 }
             }
             __threadfence_block();
-            wf2_push(S, hard ? ((cycle & 1) ? WF2_Q_F1 : WF2_Q_F0) : WF2_Q_T, fresh, s);
+            wf2_push(S, hard ? WF2_Q_F0 + (cycle & 1) : WF2_Q_T, fresh, s);
             // slots that could not be refilled die: the CTA exits when none is left
             const unsigned dead = __ballot_sync(0xffffffffu, active && !fresh);
             if (dead && lane == 0) atomicSub(&S.live, __popc(dead));
-        } else if (stage != WF2_Q_A && stage != WF2_Q_B) {
-            // ===================== T: trace the pending ray ========================================
-            // T runs the scene program (planes, spheres, small meshes, box tests); rays that enter the
-            // box of a large mesh instance continue in M (wf2_mesh_stage), which traverses the mesh
-            // BVHs -- the long, divergent part of a trace -- with per-lane refill.
-            bool isExt = false, isNee = false, toMesh = false;
+        } else if (stage == WF2_Q_T || stage >= WF2_Q_F0) {
+            // ===================== T: trace the pending ray =======================================
+            bool isExt = false, isNee = false;
             if (active) {
                 const uint32_t fl = S.flags[s];
+                V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
+                V3 d = v3(S.dx[s], S.dy[s], S.dz[s]);
                 const float time = S.time[s];
                 isExt = ((fl >> 3) & 1u) == WF2_PH_EXT;
                 isNee = !isExt;
-                V3 o, d;
-                wf2_pending_ray(S, s, isExt, o, d);
+                if (isNee) {
+                    // shadow ray from the surface point: origin = p + FaceForward(n, wi)*eps (render.cpp:121,170)
+                    const V3 p = o + d * S.ht[s];
+                    const V3 nn = v3(S.hnx[s], S.hny[s], S.hnz[s]);
+                    d = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
+                    o = p + face_forward(nn, d) * TB_RAY_EPS;
+                }
                 if (isNee || maxDepth > 0) {
-                    TracePartial tp;
-                    trace_program(sc, o, d, time, tp);
-                    toMesh = tp.meshMask != 0u && !tp.ordered;
-                    if (toMesh) {
-                        // park the partial result in the record the final hit will overwrite (an
-                        // extension ray's old hit record is dead; a shadow ray has its own fields)
-                        if (isExt) {
-                            S.ht[s] = tp.minT;
-                            S.hprim[s] = tp.closest;
-                        } else {
-                            S.st[s] = tp.minT;
-                            S.sprim[s] = tp.closest;
-                        }
-                        S.tmask[s] = tp.meshMask | (tp.tie ? 1u << 16 : 0u);
-                        isExt = isNee = false;
+                    // one traversal instance serves both ray kinds (normals only for extension rays)
+                    const Hit h = trace_closest(sc, o, d, time, isExt);
+                    if (isExt) {
+                        S.ht[s] = h.t;
+                        S.hnx[s] = h.n.x; S.hny[s] = h.n.y; S.hnz[s] = h.n.z;
+                        S.hprim[s] = h.prim;
                     } else {
-                        const Hit h = trace_finish(sc, o, d, time, isExt, tp);
-                        if (isExt) {
-                            S.ht[s] = h.t;
-                            S.hnx[s] = h.n.x; S.hny[s] = h.n.y; S.hnz[s] = h.n.z;
-                            S.hprim[s] = h.prim;
-                        } else {
-                            S.st[s] = h.t;
-                            S.sprim[s] = h.prim;
-                        }
+                        S.st[s] = h.t;
+                        S.sprim[s] = h.prim;
                     }
                 } else {
                     S.hprim[s] = -2;   // maxDepth == 0: no trace at all, radiance stays 0
                 }
             }
             __threadfence_block();
-            wf2_push(S, hard ? ((cycle & 1) ? WF2_Q_M1 : WF2_Q_M0) : WF2_Q_M0, toMesh, s);
             wf2_push(S, WF2_Q_A, isExt, s);
             wf2_push(S, WF2_Q_B, isNee, s);
         } else if (stage == WF2_Q_A) {
