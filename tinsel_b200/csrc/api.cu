@@ -359,12 +359,18 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
         meshes[m].rootRef = root;
     }
     if (!upload(meshes, &r->dMeshes, h2d)) return false;
-    // Scheduling mode of the wavefront kernel: free-running warps when ray cost varies a lot (a deep
-    // mesh BVH), block-synchronous stages otherwise.  TINSEL_B200_SCHED=hard|free overrides.
+    // Scheduling mode of the wavefront kernel (measured, profiles/README.md): block-synchronous
+    // stages win when every surface hit spawns several shadow rays (the shade and trace stages then
+    // alternate several times per bounce and the barrier keeps all warps on one stage's code);
+    // free-running warps win otherwise, and by a wide margin when ray cost varies (deep mesh BVHs).
+    // TINSEL_B200_SCHED=hard|free overrides.
     {
         int maxTris = 0;
         for (int m = 0; m < s->numMeshes; ++m) maxTris = std::max(maxTris, s->meshes[m].numIndices / 3);
-        r->hardPhases = maxTris > 4096 ? 0 : 1;
+        int numNee = s->sky.probeValid ? 1 : 0;
+        for (int i = 0; i < s->numPrimitives; ++i)
+            if (s->primitives[i].lightSamples > 0) numNee += s->primitives[i].lightSamples;
+        r->hardPhases = (numNee > 1 && maxTris <= 4096) ? 1 : 0;
         const char* sched = getenv("TINSEL_B200_SCHED");
         if (sched && strcmp(sched, "hard") == 0) r->hardPhases = 1;
         if (sched && strcmp(sched, "free") == 0) r->hardPhases = 0;
