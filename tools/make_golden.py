@@ -35,6 +35,8 @@ FRAMES = {
     "conservation": (32, 16, (0,)),
     "ajax": (48, 48, (0, 4)),
     "env": (48, 48, (0, 4)),
+    "many": (48, 32, (0, 2)),
+    "mini": (48, 32, (0, 2)),
 }
 
 f32p = C.POINTER(C.c_float)

@@ -30,6 +30,9 @@ SCENES = {
     "motionblur": ("motionblur.tin", 0, 0),
     "gloss": ("gloss.tin", 0, 0),
     "emitter": ("emitter.tin", 0, 0),
+    # this repository's own .tin scenes (tests/data): >16 primitives / a glass sphere under a gradient sky
+    "many": ("@tests/data/many.tin", 0, 0),
+    "mini": ("@tests/data/mini0.tin", 0, 0),
 }
 
 
@@ -37,7 +40,7 @@ def main(names):
     os.makedirs(os.path.join(ROOT, "scenes"), exist_ok=True)
     for name in names:
         tin, w, h = SCENES[name]
-        path = os.path.join(refdrv.REFERENCE_ROOT, "data", tin)
+        path = os.path.join(ROOT, tin[1:]) if tin.startswith("@") else os.path.join(refdrv.REFERENCE_ROOT, "data", tin)
         rs = refdrv.RefScene.from_tin(path, w, h, flavour="literal")
         out = os.path.join(ROOT, "scenes", name + ".tsnap")
         rs.save_snapshot(out)
