@@ -275,6 +275,15 @@ struct tb200_renderer {
     unsigned long long* dCounter = nullptr;
     int frame = 0;
 
+    // streamed read-back (tb200_render): band counters on the device, completion flags in mapped
+    // host memory, a private copy stream
+    unsigned int* dBandCount = nullptr;
+    volatile unsigned int* hBandFlags = nullptr;
+    unsigned int* dBandFlags = nullptr;   // device alias of hBandFlags
+    cudaStream_t copyStream = nullptr;
+    unsigned int bandTag = 0;
+    int streamedReadback = 1;             // TINSEL_B200_READBACK=plain turns it off
+
     // host read-back
     void* registered = nullptr;   // host pointer currently pinned with cudaHostRegister
     size_t registeredBytes = 0;
@@ -305,6 +314,11 @@ void free_device(tb200_renderer* r)
     cudaFree(r->dRaster);
     cudaFree(r->dCounter);
     r->dCounter = nullptr;
+    cudaFree(r->dBandCount);
+    r->dBandCount = nullptr;
+    if (r->hBandFlags) cudaFreeHost((void*)r->hBandFlags);
+    r->hBandFlags = nullptr;
+    r->dBandFlags = nullptr;
     r->dPrims = nullptr;
     r->dScenePairs = nullptr;
     r->dMeshes = nullptr;
@@ -531,10 +545,10 @@ bool finish_timing(tb200_renderer* r)
     return true;
 }
 
-// device -> host copy of the accumulator.  A host buffer that is handed in twice in a row
-// (tinsel's main.cpp passes the same g_pixels every call, src/main.cpp:249) is pinned with
-// cudaHostRegister so the copy runs at PCIe speed instead of through the pageable path.
-bool read_back(tb200_renderer* r, float* output)
+// A host buffer that is handed in twice in a row (tinsel's main.cpp passes the same g_pixels every
+// call, src/main.cpp:249) is pinned with cudaHostRegister so the copies run at PCIe speed and
+// asynchronously instead of through the pageable path.
+void pin_output(tb200_renderer* r, float* output)
 {
     const size_t bytes = size_t(r->width) * r->height * sizeof(float4);
     if (output == r->lastOutput && r->registered != output) {
@@ -550,9 +564,70 @@ bool read_back(tb200_renderer* r, float* output)
         }
     }
     r->lastOutput = output;
+}
+
+// device -> host copy of the whole accumulator after the stream's work
+bool read_back(tb200_renderer* r, float* output)
+{
+    const size_t bytes = size_t(r->width) * r->height * sizeof(float4);
+    pin_output(r, output);
     TB_CUDA(cudaMemcpyAsync(output, r->boundAccum ? r->boundAccum : r->dAccum, bytes, cudaMemcpyDeviceToHost, r->stream));
     TB_CUDA(cudaStreamSynchronize(r->stream));
     r->stats.d2hBytes += bytes;
+    return true;
+}
+
+// One frame of the wavefront kernel with the read-back streamed underneath it: samples are handed
+// out in tile-row order, the kernel flags each band of tile rows as its last sample retires
+// (wavefront2.cuh, wf2_band_report), and this thread copies every pixel row that no unfinished
+// sample can still touch while the kernel is tracing the rest.  What is left when the kernel ends
+// is the last band or two instead of the whole W*H*16 bytes.
+bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output)
+{
+    pin_output(r, output);
+    const float4* accum = P.accum;
+    const size_t rowBytes = size_t(r->width) * sizeof(float4);
+    // bands of whole tile rows, at most TB_MAX_BANDS, about 1 MiB each
+    int bandTileRows = std::max(1, (int)((size_t(1) << 20) / (rowBytes * 4)));
+    bandTileRows = std::max(bandTileRows, (P.tileRows + TB_MAX_BANDS - 1) / TB_MAX_BANDS);
+    const int numBands = (P.tileRows + bandTileRows - 1) / bandTileRows;
+    // pixel rows a sample of row y splats into: y - reach .. y + reach (render.cpp:404-407)
+    const int reach = (int)ceilf(std::max(0.0f, P.film.filterWidth)) + 1;
+
+    r->bandTag += 1;
+    if (r->bandTag == 0) r->bandTag = 1;
+    P.bandCount = r->dBandCount;
+    P.bandFlags = r->dBandFlags;
+    P.bandSamples = (unsigned)bandTileRows * (unsigned)P.tilesX * 32u;
+    P.bandTag = r->bandTag;
+    TB_CUDA(cudaMemsetAsync(r->dBandCount, 0, TB_MAX_BANDS * sizeof(unsigned int), r->stream));
+    if (!launch_frames(r, P)) return false;
+
+    int done = 0;        // bands 0..done-1 are complete
+    int copied = 0;      // pixel rows [0, copied) are already on their way to the host
+    bool copyFailed = false;
+    auto copy_rows_below = [&](int limit) {
+        limit = std::min(limit, r->height);
+        if (limit <= copied) return;
+        if (cudaMemcpyAsync((char*)output + size_t(copied) * rowBytes, (const char*)accum + size_t(copied) * rowBytes,
+                            size_t(limit - copied) * rowBytes, cudaMemcpyDeviceToHost, r->copyStream) != cudaSuccess)
+            copyFailed = true;
+        copied = limit;
+    };
+    for (;;) {
+        while (done < numBands && r->hBandFlags[done] == r->bandTag) ++done;
+        if (done >= numBands) break;
+        // unfinished samples sit in local tile rows >= done*bandTileRows, i.e. global pixel rows
+        // >= done*bandTileRows*numShards*4 (decode_sample)
+        copy_rows_below(done * bandTileRows * P.numShards * 4 - reach);
+        if (cudaEventQuery(r->evStop) != cudaErrorNotReady) break;   // finished (or failed): stop polling
+        __builtin_ia32_pause();
+    }
+    TB_CUDA(cudaStreamSynchronize(r->stream));
+    copy_rows_below(r->height);
+    TB_CUDA(cudaStreamSynchronize(r->copyStream));
+    if (copyFailed) TB_CUDA(cudaErrorUnknown);
+    r->stats.d2hBytes += size_t(r->height) * rowBytes;
     return true;
 }
 
@@ -600,11 +675,21 @@ tb200_renderer* tb200_create(const tb200_scene* scene, int device)
     }
     const char* pipe = getenv("TINSEL_B200_PIPELINE");
     if (pipe && strcmp(pipe, "mega") == 0) r->pipeline = 0;
-    if (cudaMalloc((void**)&r->dCounter, sizeof(unsigned long long)) != cudaSuccess) {
+    const char* rb = getenv("TINSEL_B200_READBACK");
+    if (rb && strcmp(rb, "plain") == 0) r->streamedReadback = 0;
+    unsigned int* hostFlags = nullptr;
+    if (cudaMalloc((void**)&r->dCounter, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void**)&r->dBandCount, TB_MAX_BANDS * sizeof(unsigned int)) != cudaSuccess ||
+        cudaHostAlloc((void**)&hostFlags, TB_MAX_BANDS * sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&r->dBandFlags, hostFlags, 0) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("tb200_create: counter allocation failed");
+        if (hostFlags) cudaFreeHost(hostFlags);
         tb200_destroy(r);
         return nullptr;
     }
+    memset(hostFlags, 0, TB_MAX_BANDS * sizeof(unsigned int));
+    r->hBandFlags = hostFlags;
     if (!build_scene(r, scene)) {
         tb200_destroy(r);
         return nullptr;
@@ -669,9 +754,20 @@ int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     } else {
         P.frame0 = r->frame;
         P.numFrames = 1;
-        if (!launch_frames(r, P)) return -1;
+        const bool streamed = r->streamedReadback && r->pipeline != 0 && P.samplesPerFrame > 0 && P.samplesPerFrame < 0x7fffffffull;
+        if (streamed) {
+            if (!render_streamed(r, P, output)) return -1;
+        } else if (!launch_frames(r, P)) {
+            return -1;
+        }
         r->frame += 1;
         r->stats.frames += 1;
+        if (streamed) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, r->evStart, r->evStop);
+            r->stats.gpuMs = ms;
+            return 0;
+        }
     }
     if (!read_back(r, output)) return -1;
     float ms = 0.0f;
@@ -818,6 +914,7 @@ void tb200_destroy(tb200_renderer* r)
     if (r->evStart) cudaEventDestroy(r->evStart);
     if (r->evStop) cudaEventDestroy(r->evStop);
     if (r->stream) cudaStreamDestroy(r->stream);
+    if (r->copyStream) cudaStreamDestroy(r->copyStream);
     delete r;
 }
 

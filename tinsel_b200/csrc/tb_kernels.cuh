@@ -21,7 +21,17 @@ struct LaunchParams {
     // tb200_trace_frame outputs (nullptr in normal rendering)
     float* outRadiance;   // 3 floats per pixel
     float* outRaster;     // 2 floats per pixel
+    // streamed read-back (tb200_render, single-frame launches; nullptr/0 otherwise): the sample range
+    // is cut into bands of `bandSamples` consecutive indices (whole tile rows); the thread that
+    // retires the last sample of a band stores `bandTag` into bandFlags[band] (mapped host memory),
+    // so the host can copy finished rows while the kernel is still tracing the rest.
+    unsigned int* bandCount;          // device counters, zeroed before the launch
+    volatile unsigned int* bandFlags; // device pointer to pinned, mapped host memory
+    unsigned int bandSamples;
+    unsigned int bandTag;
 };
+
+#define TB_MAX_BANDS 64
 
 // fills tilesX / tileRows / samplesPerFrame from the row range and shard
 void finalize_params(LaunchParams* p);

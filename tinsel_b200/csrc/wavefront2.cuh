@@ -194,6 +194,38 @@ TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s)
     return sf;
 }
 
+// Streamed read-back bookkeeping (LaunchParams::bandFlags): called by a whole warp after its lanes
+// with `have` set have retired sample `idx` (splatted it, or skipped it as tile padding).  Every
+// lane fences its own framebuffer reductions, equal bands are counted with one atomic, and whoever
+// completes a band publishes it to the host.
+static __device__ __noinline__ void wf2_band_report(unsigned int* bandCount, volatile unsigned int* bandFlags, uint32_t bandSamples,
+                                                    uint32_t samplesPerFrame, uint32_t bandTag, uint32_t idx, bool have)
+{
+    __threadfence();
+    const unsigned act = __ballot_sync(0xffffffffu, have);
+    if (!have) return;
+    const uint32_t band = idx / bandSamples;
+    const unsigned peers = __match_any_sync(act, band);
+    if ((int)(threadIdx.x & 31u) != __ffs(peers) - 1) return;
+    const uint32_t n = (uint32_t)__popc(peers);
+    const uint32_t size = min(bandSamples, samplesPerFrame - band * bandSamples);
+    if (atomicAdd(&bandCount[band], n) + n == size) {
+        __threadfence_system();
+        bandFlags[band] = bandTag;
+    }
+}
+
+static __device__ __noinline__ void wf2_band_pad(unsigned int* bandCount, volatile unsigned int* bandFlags, uint32_t bandSamples,
+                                                 uint32_t samplesPerFrame, uint32_t bandTag, uint32_t idx)
+{
+    const uint32_t band = idx / bandSamples;
+    const uint32_t size = min(bandSamples, samplesPerFrame - band * bandSamples);
+    if (atomicAdd(&bandCount[band], 1u) + 1u == size) {
+        __threadfence_system();
+        bandFlags[band] = bandTag;
+    }
+}
+
 TB_DEV void wf2_store_shadow(Wf2Shared& S, int s, const ShadowRay& sr, const NeeCursor& c)
 {
     S.sdx[s] = sr.d.x; S.sdy[s] = sr.d.y; S.sdz[s] = sr.d.z;
@@ -392,8 +424,11 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                 rx += px;
                 ry += py;
                 sample_end(P, px, py, rx, ry, v3(S.Lx[s], S.Ly[s], S.Lz[s]));
-                S.sample[s] = 0xffffffffu;
             }
+            if (P.bandFlags)
+                wf2_band_report(P.bandCount, P.bandFlags, P.bandSamples, (uint32_t)P.samplesPerFrame, P.bandTag, S.sample[s],
+                                active && S.sample[s] != 0xffffffffu);
+            if (active) S.sample[s] = 0xffffffffu;
             // claim a new sample; indices on tile padding outside the image are skipped
             bool want = active && !*(volatile int*)&S.exhausted;
             bool fresh = false;
@@ -431,6 +466,9 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
                             S.flags[s] = ((uint32_t)TB_REFLECTED << 1) | ((uint32_t)WF2_PH_EXT << 3);
                             fresh = true;
                             want = false;
+                        } else if (P.bandFlags) {
+                            // tile padding outside the image retires at once
+                            wf2_band_pad(P.bandCount, P.bandFlags, P.bandSamples, (uint32_t)P.samplesPerFrame, P.bandTag, (uint32_t)idx);
                         }
                     }
                 }
