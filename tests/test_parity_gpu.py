@@ -27,6 +27,7 @@ SCENES = {
     "env": (160, 160),
     "many": (120, 80),     # 22 primitives: reference-order BVH walk instead of the flat scene program
     "mini": (96, 64),      # glass sphere (specular transmission, Beer-Lambert medium) under a gradient sky
+    "envmini": (128, 96),  # HDR-probe lighting only (synthetic 128x64 probe): ProbeSample / ProbePdf / ProbeEval
 }
 
 
@@ -76,7 +77,7 @@ def test_per_sample_radiance_bit_exact(name, pipeline):
 
 
 @pytest.mark.parametrize("pipeline", ["mega", "wavefront"])
-@pytest.mark.parametrize("name", ["cornell", "veach", "glass", "ajax", "env"])
+@pytest.mark.parametrize("name", ["cornell", "veach", "glass", "ajax", "env", "envmini"])
 def test_render_matches_seeded_oracle(name, pipeline):
     """Renderer.Render x spp vs oracle B at matched spp and seeds: rel-L2 <= 1e-4 (BASELINE.json)."""
     snap, cam, opt, ref, r = _setup(name, pipeline)
@@ -305,6 +306,33 @@ def test_streamed_readback_delivers_final_rows(case):
     assert np.allclose(out, outp, rtol=2e-5, atol=1e-6)
     assert r.stats().samples == rp.stats().samples
     rp.close()
+    r.close()
+    ref.close()
+    snap.close()
+
+
+# BASELINE.json configs at their full image sizes (C2 cornell 1024^2, C3 ajax 1024^2, C4 veach
+# 1920x1080 with clamp 4, C5 env 2048^2): one frame of every config traced per sample on the GPU
+# and by the reference's PathTrace on all host cores -- bit-exact -- and the same frame through
+# Render() against the seeded oracle image.
+@pytest.mark.parametrize("name,size", [("cornell", (1024, 1024)), ("ajax", (1024, 1024)), ("veach", (1920, 1080)),
+                                       ("env", (2048, 2048))])
+def test_baseline_configs_full_size(name, size):
+    snap, cam, opt, ref, r = _setup(name, "wavefront", size=size)
+    threads = os.cpu_count() or 8
+    frame = 3
+    rad, ras = r.trace_frame(cam, opt, frame)
+    rrad, rras = ref.trace_frame(frame, nthreads=threads)
+    assert np.array_equal(ras, rras)
+    same = (rad.view(np.uint32) == rrad.view(np.uint32)).all(-1) | (np.isnan(rad).any(-1) & np.isnan(rrad).any(-1))
+    assert bool(same.all()), "%d of %d samples differ" % (int((~same).sum()), same.size)
+    out = np.zeros((opt.height, opt.width, 4), np.float32)
+    r.Render(cam, opt, out)
+    r.Render(cam, opt, out)
+    oracle = ref.render_seeded(0, 2, nthreads=threads)
+    num = np.linalg.norm((out - oracle).astype(np.float64))
+    den = np.linalg.norm(oracle.astype(np.float64))
+    assert num / den <= 1e-4, "rel L2 %g" % (num / den)
     r.close()
     ref.close()
     snap.close()

@@ -65,5 +65,6 @@ if __name__ == "__main__":
         if os.path.exists(out):
             old = json.load(open(out))
         res["dram_traffic_bytes_per_launch"] = old.get("dram_traffic_bytes_per_launch")
+        res["dram_traffic_source"] = old.get("dram_traffic_source")
         json.dump(res, open(out, "w"), indent=1)
         print("wrote", out)

@@ -37,6 +37,7 @@ FRAMES = {
     "env": (48, 48, (0, 4)),
     "many": (48, 32, (0, 2)),
     "mini": (48, 32, (0, 2)),
+    "envmini": (64, 48, (0, 3)),
 }
 
 f32p = C.POINTER(C.c_float)
@@ -46,8 +47,10 @@ def fp(a):
     return a.ctypes.data_as(f32p)
 
 
-def scene_fixtures():
+def scene_fixtures(only=()):
     for name, (w, h, frames) in FRAMES.items():
+        if only and name not in only:
+            continue
         path = tb.scene_path(name)
         if not os.path.exists(path):
             print("skip", name)
@@ -173,6 +176,8 @@ def kat_fixtures():
 
 
 if __name__ == "__main__":
+    # python tools/make_golden.py [scene ...]: no arguments regenerates everything
     os.makedirs(GOLD, exist_ok=True)
-    kat_fixtures()
-    scene_fixtures()
+    if len(sys.argv) == 1:
+        kat_fixtures()
+    scene_fixtures(sys.argv[1:])

@@ -33,6 +33,8 @@ SCENES = {
     # this repository's own .tin scenes (tests/data): >16 primitives / a glass sphere under a gradient sky
     "many": ("@tests/data/many.tin", 0, 0),
     "mini": ("@tests/data/mini0.tin", 0, 0),
+    # small synthetic HDR probe (tools/make_test_probe.py): the image-based-lighting path in a snapshot small enough to commit
+    "envmini": ("@tests/data/envmini.tin", 0, 0),
 }
 
 
