@@ -221,4 +221,99 @@ TBM_HD float tbm_acosf(float xf)
     return (float)tbm_atan2_d(s, x);
 }
 
+/* ---- powf ----------------------------------------------------------------------------------
+ * Used by the display/finish step (ToneMap -> SrgbToLinear -> LinearToSrgb, util.h:25-42,
+ * maths.h:1545-1555): pow(x, y) = exp(y * log x) evaluated in double, rounded once to float. */
+
+/* e^x in double for |x| <= 745 (same reduction and polynomial as tbm_expf) */
+TBM_HD double tbm_exp_d(double x)
+{
+    const double kd = rint(TBM_MUL(x, 1.4426950408889634 /* log2(e) */));
+    double r = TBM_SUB(x, TBM_MUL(kd, 0.6931471803691238));
+    r = TBM_SUB(r, TBM_MUL(kd, 1.9082149292705877e-10));
+    double p = 1.6059043836821613e-10;           /* 1/13! */
+    p = TBM_HORNER(p, r, 2.0876756987868100e-09); /* 1/12! */
+    p = TBM_HORNER(p, r, 2.5052108385441720e-08); /* 1/11! */
+    p = TBM_HORNER(p, r, 2.7557319223985888e-07); /* 1/10! */
+    p = TBM_HORNER(p, r, 2.7557319223985893e-06); /* 1/9!  */
+    p = TBM_HORNER(p, r, 2.4801587301587302e-05); /* 1/8!  */
+    p = TBM_HORNER(p, r, 1.9841269841269841e-04); /* 1/7!  */
+    p = TBM_HORNER(p, r, 1.3888888888888889e-03); /* 1/6!  */
+    p = TBM_HORNER(p, r, 8.3333333333333332e-03); /* 1/5!  */
+    p = TBM_HORNER(p, r, 4.1666666666666664e-02); /* 1/4!  */
+    p = TBM_HORNER(p, r, 1.6666666666666666e-01); /* 1/3!  */
+    p = TBM_HORNER(p, r, 0.5);
+    p = TBM_HORNER(p, r, 1.0);
+    p = TBM_HORNER(p, r, 1.0);
+    /* 2^k in two factors so that results in the float-denormal range stay exact powers of two */
+    const int k = (int)kd;
+    const int k1 = k / 2, k2 = k - k1;
+    const double s1 = tbm_bits_to_double((uint64_t)(k1 + 1023) << 52);
+    const double s2 = tbm_bits_to_double((uint64_t)(k2 + 1023) << 52);
+    return TBM_MUL(TBM_MUL(p, s1), s2);
+}
+
+/* log x in double for finite x > 0 (x a normal double): x = m 2^e, m in [sqrt(.5), sqrt 2),
+ * log m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716, odd series to s^25 */
+TBM_HD double tbm_log_d(double x)
+{
+    uint64_t u;
+#if defined(__CUDA_ARCH__)
+    u = (uint64_t)__double_as_longlong(x);
+#else
+    memcpy(&u, &x, sizeof(u));
+#endif
+    int e = (int)((u >> 52) & 0x7ffu) - 1023;
+    uint64_t mant = u & 0x000fffffffffffffull;
+    /* mantissa bits above sqrt(2)-1 go to the next binade: m in [sqrt(.5), sqrt 2) */
+    if (mant > 0x6a09e667f3bcdull) e += 1;
+    const double m = tbm_bits_to_double(mant | ((mant > 0x6a09e667f3bcdull ? 1022ull : 1023ull) << 52));
+    const double f = TBM_SUB(m, 1.0);
+    const double sq = TBM_DIV(f, TBM_ADD(m, 1.0));
+    const double z = TBM_MUL(sq, sq);
+    double p = 8.0000000000000002e-02;            /* 2/25 */
+    p = TBM_HORNER(p, z, 8.6956521739130432e-02); /* 2/23 */
+    p = TBM_HORNER(p, z, 9.5238095238095233e-02); /* 2/21 */
+    p = TBM_HORNER(p, z, 1.0526315789473684e-01); /* 2/19 */
+    p = TBM_HORNER(p, z, 1.1764705882352941e-01); /* 2/17 */
+    p = TBM_HORNER(p, z, 1.3333333333333333e-01); /* 2/15 */
+    p = TBM_HORNER(p, z, 1.5384615384615385e-01); /* 2/13 */
+    p = TBM_HORNER(p, z, 1.8181818181818182e-01); /* 2/11 */
+    p = TBM_HORNER(p, z, 2.2222222222222221e-01); /* 2/9  */
+    p = TBM_HORNER(p, z, 2.8571428571428570e-01); /* 2/7  */
+    p = TBM_HORNER(p, z, 4.0000000000000002e-01); /* 2/5  */
+    p = TBM_HORNER(p, z, 6.6666666666666663e-01); /* 2/3  */
+    /* log m = 2 s + s^3 p */
+    const double lm = TBM_ADD(TBM_MUL(2.0, sq), TBM_MUL(TBM_MUL(sq, z), p));
+    const double ed = (double)e;
+    return TBM_ADD(TBM_MUL(ed, 0.6931471803691238), TBM_ADD(TBM_MUL(ed, 1.9082149292705877e-10), lm));
+}
+
+TBM_HD float tbm_powf(float xf, float yf)
+{
+    const double x = (double)xf, y = (double)yf;
+    const double kInfD = tbm_bits_to_double(0x7ff0000000000000ull);
+    if (y == 0.0 || x == 1.0) return 1.0f;                     /* C99: also for NaN in the other argument */
+    if (!(x == x) || !(y == y)) return xf + yf;
+    const int yIsInt = (fabs(y) >= 9007199254740992.0) || (rint(y) == y);
+    const int yIsOdd = yIsInt && fabs(y) < 9007199254740992.0 && (rint(TBM_MUL(y, 0.5)) != TBM_MUL(y, 0.5));
+    if (fabs(y) == kInfD) {
+        const double ax = fabs(x);
+        if (ax == 1.0) return 1.0f;
+        return ((ax > 1.0) == (y > 0.0)) ? (float)kInfD : 0.0f;
+    }
+    if (x == 0.0 || fabs(x) == kInfD) {
+        const int big = (fabs(x) == kInfD) == (y > 0.0);       /* result magnitude inf (else 0) */
+        const double mag = big ? kInfD : 0.0;
+        return (float)((signbit(x) && yIsOdd) ? -mag : mag);
+    }
+    if (x < 0.0 && !yIsInt) return (float)tbm_bits_to_double(0x7ff8000000000000ull);
+    const double t = TBM_MUL(y, tbm_log_d(fabs(x)));
+    double r;
+    if (t > 100.0) r = kInfD;
+    else if (t < -110.0) r = 0.0;
+    else r = tbm_exp_d(t);
+    return (float)((x < 0.0 && yIsOdd) ? -r : r);
+}
+
 #endif /* TB200_DETMATH_H */

@@ -201,6 +201,24 @@ float* tb200_device_accumulator(tb200_renderer* r);
 /* Copies the accumulator to host memory (width*height*4 floats).  Returns 0 on success. */
 int tb200_read_accumulator(tb200_renderer* r, float* output);
 
+/* `n` x tb200_render in one call with ONE read-back: adds frames k..k+n-1 (the per-sample seeds of
+ * n consecutive Render calls) and leaves the running sums in `output` (HOST, width*height*4
+ * floats).  Replaces the `for (i < numSamples) g_renderer->Render(...)` loop of src/main.cpp:242-251
+ * (16 calls, 16 read-backs per displayed frame).  ePathTrace only.  Returns 0 on success. */
+int tb200_render_n(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int n, float* output);
+
+/* The display/finish step that follows the path in src/main.cpp:258-271 and src/png.cpp:329-343,
+ * on the device, reading the accumulator where it lies:
+ *   filtered[i] = LinearToSrgb(ToneMap(pixels[i] * (exposure / pixels[i].w), limit))
+ *                 (util.h:25-42 filmic curve, maths.h:1545-1555; alpha comes out 0 as in the reference)
+ *   rgb8[i*3+c] = Quantize(filtered[i][c]*255.0 + Randf + Randf - 0.5f)  with WritePng's own
+ *                 sequential Random() dither stream (6 draws per pixel, pixel-major)
+ * `filtered` (HOST, width*height*4 floats) and `rgb8` (HOST, width*height*3 bytes) are each
+ * optional (NULL = not wanted): a caller that only displays or writes the PNG reads back 3 bytes
+ * per pixel instead of 16.  Arithmetic is the reference's expression order with powf from
+ * include/tb200_detmath.h.  Returns 0 on success. */
+int tb200_finish(tb200_renderer* r, float exposure, float limit, float* filtered, unsigned char* rgb8);
+
 /* Per-sample radiance probe used by the parity tests: traces frame `frame` only and writes,
  * for pixel p (row-major), radiance[3p..3p+2] = PathTrace() result and raster[2p..2p+1] =
  * jittered raster position, WITHOUT touching the accumulator.  Host pointers.  0 on success. */

@@ -35,6 +35,7 @@ static inline double tb_shim_atan2(double y, double x) { return ::atan2(y, x); }
 #define expf tbm_expf
 #define acosf tbm_acosf
 #define atan2f tbm_atan2f
+#define powf tbm_powf
 #define sin tb_shim_sin
 #define cos tb_shim_cos
 #define atan2 tb_shim_atan2

@@ -21,6 +21,8 @@
 //                        (pixel, frame) by tb200_sample_seed(), calling the reference's PathTrace
 //                        and CpuRenderer::AddSample.  This is the parity oracle ("oracle B").
 //   ref_trace_frame      per-sample radiance + raster position for one frame, no filtering.
+//   ref_finish           the display loop of src/main.cpp:262-271 over the reference's own ToneMap /
+//                        LinearToSrgb (util.h, maths.h); ref_write_png = the reference's WritePng.
 //   ref_*                known-answer hooks for single functions (Random, BSDF*, GenerateRay, ...).
 #include <cstring>
 #include <cstdio>
@@ -33,6 +35,7 @@
 
 #include "render.cpp"  // the reference's src/render.cpp (via -I/root/reference/src)
 #include "loader.h"
+#include "png.h"
 
 #include "tinsel_b200.h"
 
@@ -381,6 +384,23 @@ void ref_render_seeded(void* h, int frame0, int nframes, float* out, int nthread
         for (int y = b0; y < b1; ++y)
             for (int x = 0; x < W; ++x) o[y * W + x] += bufs[t][size_t(y - b0) * W + x];
     }
+}
+
+// The finish loop of src/main.cpp:262-271, statement for statement, over caller-supplied sums.
+void ref_finish(const float* pixels, int numPixels, float exposure, float limit, float* filtered)
+{
+    const Color* g_pixels = (const Color*)pixels;
+    Color* g_filtered = (Color*)filtered;
+    for (int i = 0; i < numPixels; ++i) {
+        float s = exposure / g_pixels[i].w;
+        g_filtered[i] = LinearToSrgb(ToneMap(g_pixels[i] * s, limit));
+    }
+}
+
+// The reference's own PNG writer (src/png.cpp:329-371): dithered 8-bit quantisation + TinyPngOut.
+void ref_write_png(const float* filtered, int width, int height, const char* path)
+{
+    WritePng((const Color*)filtered, width, height, path);
 }
 
 // One frame, no filtering: radiance[3p..] = PathTrace result, raster[2p..] = (x,y) of pixel p.

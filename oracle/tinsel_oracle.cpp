@@ -1085,4 +1085,42 @@ void oracle_primitive_sample(void* h, int prim, float time, int seed, float* pos
     *area = prim_area(sc, sc.primitives[prim]);
 }
 
+// ---- display/finish step ------------------------------------------------------
+// src/main.cpp:262-271: s = exposure / w;  filtered = LinearToSrgb(ToneMap(pixel * s, limit)),
+// ToneMap = filmic curve of util.h:25-42 then SrgbToLinear (maths.h:1551-1555), alpha 0.
+static float finish_channel(float t)
+{
+    float b = t - 0.004f;
+    float x = (0.0f < b) ? b : 0.0f;                           // Max(Vec3(0), c - Vec3(0.004)), maths.h:59
+    float ret = (x * (6.2f * x + 0.5f)) / (x * (6.2f * x + 1.7f) + 0.06f);
+    float lin = tbm_powf(ret, 2.2f);                           // SrgbToLinear, maths.h:1553-1554
+    return tbm_powf(lin, 1.0f / 2.2f);                         // LinearToSrgb, maths.h:1547-1548
+}
+void oracle_finish(const float* pixels, int numPixels, float exposure, float limit, float* filtered)
+{
+    (void)limit;   // only the commented-out Reinhard branch of ToneMap reads it
+    for (int i = 0; i < numPixels; ++i) {
+        float s = exposure / pixels[i * 4 + 3];
+        filtered[i * 4 + 0] = finish_channel(pixels[i * 4 + 0] * s);
+        filtered[i * 4 + 1] = finish_channel(pixels[i * 4 + 1] * s);
+        filtered[i * 4 + 2] = finish_channel(pixels[i * 4 + 2] * s);
+        filtered[i * 4 + 3] = 0.0f;
+    }
+}
+// src/png.cpp:324-343: the 8-bit buffer WritePng hands to TinyPngOut (one sequential Random(),
+// two draws per channel; sum in double, narrowed to float, Clamp = Min(Max(x,0),255), truncated).
+void oracle_quantize(const float* filtered, int numPixels, unsigned char* rgb8)
+{
+    rng_t rand = rng_make(0u);
+    for (int i = 0; i < numPixels; ++i)
+        for (int c = 0; c < 3; ++c) {
+            float r1 = rng_f(rand);
+            float r2 = rng_f(rand);
+            float x = (float)((double)filtered[i * 4 + c] * 255.0 + (double)r1 + (double)r2 - (double)0.5f);
+            x = (x < 0.0f) ? 0.0f : x;
+            x = (x < 255.0f) ? x : 255.0f;
+            rgb8[i * 3 + c] = (unsigned char)x;
+        }
+}
+
 }  // extern "C"

@@ -77,6 +77,8 @@ def load_ref(flavour="detmath"):
     lib.ref_probe_sample.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p]
     lib.ref_sky_eval.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
     lib.ref_primitive_sample.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, _f32p, _f32p, _f32p]
+    lib.ref_finish.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
+    lib.ref_write_png.argtypes = [_f32p, C.c_int, C.c_int, C.c_char_p]
     _libs[flavour] = lib
     return lib
 
@@ -199,6 +201,8 @@ def load_port():
     lib.oracle_probe_sample.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p]
     lib.oracle_sky_eval.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
     lib.oracle_primitive_sample.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, _f32p, _f32p, _f32p]
+    lib.oracle_finish.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
+    lib.oracle_quantize.argtypes = [_f32p, C.c_int, C.POINTER(C.c_ubyte)]
     abi.declare_snapshot_api(lib)
     _port = lib
     return lib
@@ -250,3 +254,36 @@ class PortScene:
         if self.h:
             self.lib.oracle_destroy(self.h)
             self.h = None
+
+
+# ---- display/finish step (src/main.cpp:262-271, src/png.cpp:329-343) -----------------------------
+def ref_finish(pixels, exposure, limit=1.5, flavour="detmath"):
+    """The reference's own ToneMap/LinearToSrgb over `pixels` (H,W,4 running sums)."""
+    pixels = np.ascontiguousarray(pixels, np.float32)
+    out = np.empty_like(pixels)
+    load_ref(flavour).ref_finish(_fp(pixels), pixels.size // 4, exposure, limit, _fp(out))
+    return out
+
+
+def ref_png_bytes(filtered, path, flavour="detmath"):
+    """Runs the reference's WritePng on `filtered` (H,W,4) and decodes the file: (H,W,3) uint8."""
+    from PIL import Image
+    filtered = np.ascontiguousarray(filtered, np.float32)
+    h, w = filtered.shape[:2]
+    load_ref(flavour).ref_write_png(_fp(filtered), w, h, str(path).encode())
+    return np.asarray(Image.open(str(path)).convert("RGB"), dtype=np.uint8)
+
+
+def port_finish(pixels, exposure, limit=1.5):
+    pixels = np.ascontiguousarray(pixels, np.float32)
+    out = np.empty_like(pixels)
+    load_port().oracle_finish(_fp(pixels), pixels.size // 4, exposure, limit, _fp(out))
+    return out
+
+
+def port_quantize(filtered):
+    filtered = np.ascontiguousarray(filtered, np.float32)
+    h, w = filtered.shape[:2]
+    out = np.empty((h, w, 3), np.uint8)
+    load_port().oracle_quantize(_fp(filtered), h * w, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return out

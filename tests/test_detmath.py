@@ -26,9 +26,21 @@ int main(){
     float g[5]={sinf(x),cosf(x),expf(e),acosf(y),atan2f(y,p)};
     for(int k=0;k<5;k++){ if(r[k]!=d[k]) misround++; if(ulp(r[k],g[k])>1) bad++; }
   }
+  // powf over the finish step's domain (x >= 0, exponents 2.2 and 1/2.2) and general arguments
+  for(long i=0;i<n;i++){
+    float x = rnd()*rnd()*4.0f, gy = (i&1) ? 2.2f : 1.0f/2.2f, y = (rnd()*2.0f-1.0f)*8.0f;
+    float xs = ldexpf(rnd()+0.5f, (int)(rnd()*60.0f)-30);
+    float r[3]={tbm_powf(x,gy), tbm_powf(xs,y), tbm_powf(x+1e-3f, y)};
+    float d[3]={(float)pow((double)x,(double)gy),(float)pow((double)xs,(double)y),(float)pow((double)(x+1e-3f),(double)y)};
+    float g[3]={powf(x,gy),powf(xs,y),powf(x+1e-3f,y)};
+    for(int k=0;k<3;k++){ if(r[k]!=d[k]) misround++; if(ulp(r[k],g[k])>1) bad++; }
+  }
   float s1,c1; tbm_sincosf(1.25f,&s1,&c1);
   int special = tbm_expf(0.f)==1.0f && tbm_expf(-0.f)==1.0f && tbm_expf(-200.f)==0.0f && std::isinf(tbm_expf(100.f))
      && tbm_acosf(1.f)==0.0f && tbm_atan2f(0.f,-1.f)>3.14f && tbm_atan2f(-0.f,-1.f)<-3.14f && tbm_sinf(0.f)==0.f && tbm_cosf(0.f)==1.f
+     && tbm_powf(0.f,2.2f)==0.f && tbm_powf(1.f,2.2f)==1.f && tbm_powf(5.f,0.f)==1.f && std::isnan(tbm_powf(NAN,2.2f))
+     && std::isinf(tbm_powf(INFINITY,0.4545f)) && std::isnan(tbm_powf(-1.f,2.2f)) && tbm_powf(-2.f,3.f)==-8.f && tbm_powf(2.f,-2.f)==0.25f
+     && tbm_powf(0.f,-1.f)==INFINITY && tbm_powf(4.f,0.5f)==2.f && tbm_powf(1e-30f,2.2f)==powf(1e-30f,2.2f) && tbm_powf(1e30f,2.2f)==INFINITY
      && s1==tbm_sinf(1.25f) && c1==tbm_cosf(1.25f) && std::isnan(tbm_acosf(1.5f));
   printf("%ld %ld %d\n", misround, bad, special);
 }
@@ -41,6 +53,6 @@ def test_detmath_is_correctly_rounded(tmp_path):
     exe = str(tmp_path / "t")
     subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe])
     misround, bad, special = map(int, subprocess.check_output([exe]).split())
-    assert misround <= 2, "results differ from the once-rounded double libm value in %d of 1e7 calls" % misround
+    assert misround <= 4, "results differ from the once-rounded double libm value in %d of 1.6e7 calls" % misround
     assert bad == 0, "more than 1 ulp from glibc float functions"
     assert special == 1

@@ -41,6 +41,35 @@ def test_plugin_render_matches_seeded_oracle(name):
     ref.close()
 
 
+@pytest.mark.gpu
+def test_plugin_fast_paths_render_n_and_finish(tmp_path):
+    """TinselB200RenderN + TinselB200Finish (tinsel_b200_plugin.h) on a reference Scene, against the
+    reference's own finish loop and PNG writer applied to the sums the call returned."""
+    if not os.path.exists(PLUGIN) or not refdrv.have_ref("detmath"):
+        pytest.skip("plugin or oracle/_ref not built")
+    os.environ.pop("TINSEL_B200_PIPELINE", None)
+    ref = refdrv.RefScene.from_snapshot(tb.scene_path("veach"), "detmath")
+    ref.set_size(96, 80)
+    lib = C.CDLL(PLUGIN)
+    f32p = C.POINTER(C.c_float)
+    lib.tb200_plugin_present.restype = C.c_int
+    lib.tb200_plugin_present.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, f32p, f32p, C.POINTER(C.c_ubyte)]
+    out = np.zeros((80, 96, 4), np.float32)
+    filtered = np.zeros((80, 96, 4), np.float32)
+    rgb8 = np.zeros((80, 96, 3), np.uint8)
+    rc = lib.tb200_plugin_present(ref.lib.ref_native_scene(ref.h), ref.lib.ref_native_camera(ref.h), ref.lib.ref_native_options(ref.h),
+                                  6, out.ctypes.data_as(f32p), filtered.ctypes.data_as(f32p), rgb8.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    assert rc == 0
+    oracle = ref.render_seeded(0, 6, 4)
+    rel = np.linalg.norm((out - oracle).astype(np.float64)) / np.linalg.norm(oracle.astype(np.float64))
+    assert rel <= 1e-4, rel
+    exposure = float(ref.options.exposure)
+    want = refdrv.ref_finish(out, exposure)
+    assert ((filtered.view(np.uint32) == want.view(np.uint32)) | (np.isnan(filtered) & np.isnan(want))).all()
+    assert np.array_equal(rgb8, refdrv.ref_png_bytes(want, tmp_path / "v.png"))
+    ref.close()
+
+
 HEADLESS = os.path.join(tb.ROOT, "tinsel_b200", "plugin", "tinsel_headless")
 HEADLESS_CPU = os.path.join(tb.ROOT, "tinsel_b200", "plugin", "tinsel_headless_cpu")
 

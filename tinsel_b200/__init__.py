@@ -56,6 +56,10 @@ def load_library():
     lib.tb200_device_accumulator.argtypes = [C.c_void_p]
     lib.tb200_read_accumulator.restype = C.c_int
     lib.tb200_read_accumulator.argtypes = [C.c_void_p, f32p]
+    lib.tb200_render_n.restype = C.c_int
+    lib.tb200_render_n.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), C.c_int, f32p]
+    lib.tb200_finish.restype = C.c_int
+    lib.tb200_finish.argtypes = [C.c_void_p, C.c_float, C.c_float, f32p, C.POINTER(C.c_ubyte)]
     lib.tb200_trace_frame.restype = C.c_int
     lib.tb200_trace_frame.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), C.c_int, f32p, f32p]
     lib.tb200_set_frame.restype = None
@@ -163,6 +167,21 @@ class Renderer:
             out = np.empty((self.height, self.width, 4), np.float32)
         self._check(self.lib.tb200_read_accumulator(self.h, _fp(out)), "tb200_read_accumulator")
         return out
+
+    def render_n(self, camera, options, n, output):
+        """n x Render with one read-back (the `numSamples` loop of src/main.cpp:242-251)."""
+        assert output.dtype == np.float32 and output.flags["C_CONTIGUOUS"]
+        assert output.size == options.width * options.height * 4
+        self._check(self.lib.tb200_render_n(self.h, C.byref(camera), C.byref(options), n, _fp(output)), "tb200_render_n")
+
+    def finish(self, exposure, limit, filtered=True, rgb8=True):
+        """Display/finish step on the device (src/main.cpp:258-271, src/png.cpp:329-343):
+        returns (filtered float32 (H,W,4) or None, rgb8 uint8 (H,W,3) or None)."""
+        f = np.empty((self.height, self.width, 4), np.float32) if filtered else None
+        b = np.empty((self.height, self.width, 3), np.uint8) if rgb8 else None
+        self._check(self.lib.tb200_finish(self.h, exposure, limit, _fp(f) if filtered else None,
+                                          b.ctypes.data_as(C.POINTER(C.c_ubyte)) if rgb8 else None), "tb200_finish")
+        return f, b
 
     def device_accumulator_ptr(self):
         return self.lib.tb200_device_accumulator(self.h)

@@ -158,6 +158,8 @@ EXPORTS = [
     "tb200_bind_accumulator",
     "tb200_device_accumulator",
     "tb200_read_accumulator",
+    "tb200_render_n",
+    "tb200_finish",
     "tb200_trace_frame",
     "tb200_set_frame",
     "tb200_get_stats",

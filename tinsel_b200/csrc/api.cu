@@ -275,6 +275,13 @@ struct tb200_renderer {
     unsigned long long* dCounter = nullptr;
     int frame = 0;
 
+    // display/finish step (tb200_finish)
+    float4* dFiltered = nullptr;
+    unsigned char* dRgb8 = nullptr;
+    uint2* dDither = nullptr;
+    int finishWidth = 0, finishHeight = 0;   // size the three buffers above were made for
+    bool ditherReady = false;
+
     // streamed read-back (tb200_render): band counters on the device, completion flags in mapped
     // host memory, a private copy stream
     unsigned int* dBandCount = nullptr;
@@ -316,6 +323,14 @@ void free_device(tb200_renderer* r)
     r->dCounter = nullptr;
     cudaFree(r->dBandCount);
     r->dBandCount = nullptr;
+    cudaFree(r->dFiltered);
+    cudaFree(r->dRgb8);
+    cudaFree(r->dDither);
+    r->dFiltered = nullptr;
+    r->dRgb8 = nullptr;
+    r->dDither = nullptr;
+    r->finishWidth = r->finishHeight = 0;
+    r->ditherReady = false;
     if (r->hBandFlags) cudaFreeHost((void*)r->hBandFlags);
     r->hBandFlags = nullptr;
     r->dBandFlags = nullptr;
@@ -505,10 +520,10 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     return true;
 }
 
-bool launch_frames(tb200_renderer* r, LaunchParams& P)
+bool launch_frames(tb200_renderer* r, LaunchParams& P, bool recordStart = true)
 {
     unsigned long long launches = 0;
-    TB_CUDA(cudaEventRecord(r->evStart, r->stream));
+    if (recordStart) TB_CUDA(cudaEventRecord(r->evStart, r->stream));
     if (P.samplesPerFrame > 0) {
         // slot records keep a 32-bit sample index: split very long jobs into several launches
         const int framesPerLaunch = (int)std::max<unsigned long long>(1ull, 0x7fffffffull / P.samplesPerFrame);
@@ -582,7 +597,7 @@ bool read_back(tb200_renderer* r, float* output)
 // (wavefront2.cuh, wf2_band_report), and this thread copies every pixel row that no unfinished
 // sample can still touch while the kernel is tracing the rest.  What is left when the kernel ends
 // is the last band or two instead of the whole W*H*16 bytes.
-bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output)
+bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output, bool recordStart = true)
 {
     pin_output(r, output);
     const float4* accum = P.accum;
@@ -600,8 +615,9 @@ bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output)
     P.bandFlags = r->dBandFlags;
     P.bandSamples = (unsigned)bandTileRows * (unsigned)P.tilesX * 32u;
     P.bandTag = r->bandTag;
+    if (recordStart) TB_CUDA(cudaEventRecord(r->evStart, r->stream));
     TB_CUDA(cudaMemsetAsync(r->dBandCount, 0, TB_MAX_BANDS * sizeof(unsigned int), r->stream));
-    if (!launch_frames(r, P)) return false;
+    if (!launch_frames(r, P, false)) return false;
 
     int done = 0;        // bands 0..done-1 are complete
     int copied = 0;      // pixel rows [0, copied) are already on their way to the host
@@ -857,6 +873,127 @@ int tb200_read_accumulator(tb200_renderer* r, float* output)
     }
     cudaSetDevice(r->device);
     return read_back(r, output) ? 0 : -1;
+}
+
+int tb200_render_n(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int n, float* output)
+{
+    if (!r || !camera || !options || !output || n < 1) {
+        set_error("tb200_render_n: bad argument");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    if (options->mode != TB200_MODE_PATHTRACE) {
+        set_error("tb200_render_n: only ePathTrace is batched");
+        return -1;
+    }
+    LaunchParams P;
+    if (!fill_params(r, camera, options, &P)) return -1;
+    // frames k .. k+n-2 in one launch, the last one with the read-back streamed underneath it
+    const bool streamed = r->streamedReadback && r->pipeline != 0 && P.samplesPerFrame > 0 && P.samplesPerFrame < 0x7fffffffull;
+    const int head = streamed ? n - 1 : n;
+    bool started = false;
+    if (head > 0) {
+        P.frame0 = r->frame;
+        P.numFrames = head;
+        if (!launch_frames(r, P)) return -1;
+        started = true;
+    }
+    if (streamed) {
+        P.frame0 = r->frame + head;
+        P.numFrames = 1;
+        if (!render_streamed(r, P, output, !started)) return -1;
+    } else if (!read_back(r, output)) {
+        return -1;
+    }
+    r->frame += n;
+    r->stats.frames += n;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, r->evStart, r->evStop);
+    r->stats.gpuMs = ms;
+    return 0;
+}
+
+int tb200_finish(tb200_renderer* r, float exposure, float limit, float* filtered, unsigned char* rgb8)
+{
+    (void)limit;   // ToneMap's filmic branch ignores it (util.h:25-42), kept for the call shape of main.cpp:269
+    if (!r || !r->dAccum) {
+        set_error("tb200_finish: tb200_init has not been called");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    const int W = r->width, H = r->height;
+    const size_t n = size_t(W) * H;
+    const size_t rgbBytes = ((n + 3) / 4) * 12;
+    if (r->finishWidth != W || r->finishHeight != H) {
+        cudaFree(r->dFiltered);
+        cudaFree(r->dRgb8);
+        cudaFree(r->dDither);
+        r->dFiltered = nullptr;
+        r->dRgb8 = nullptr;
+        r->dDither = nullptr;
+        r->ditherReady = false;
+        r->finishWidth = r->finishHeight = 0;
+        if (cudaMalloc((void**)&r->dFiltered, n * sizeof(float4)) != cudaSuccess ||
+            cudaMalloc((void**)&r->dRgb8, rgbBytes) != cudaSuccess ||
+            cudaMalloc((void**)&r->dDither, n * sizeof(uint2)) != cudaSuccess) {
+            set_error("tb200_finish: buffer allocation failed");
+            return -1;
+        }
+        r->finishWidth = W;
+        r->finishHeight = H;
+    }
+    if (rgb8 && !r->ditherReady) {
+        // WritePng (png.cpp:329-343) draws its dither from one sequential Random(): six draws per pixel
+        // in pixel order.  The stream does not depend on the image, so the state in front of every
+        // pixel is tabulated once per image size and the kernel continues from there.
+        std::vector<uint2> states(n);
+        uint32_t s1 = 315645664u, s2 = s1 ^ 0x13ab45feu;   // Random(0), maths.h:1041-1045
+        for (size_t i = 0; i < n; ++i) {
+            states[i] = make_uint2(s1, s2);
+            for (int k = 0; k < 6; ++k) {
+                const uint32_t a = s1, b = s2;
+                s1 = (b ^ ((a << 5) | (a >> 27))) ^ (a * b);
+                s2 = s1 ^ ((b << 12) | (b >> 20));
+            }
+        }
+        if (cudaMemcpyAsync(r->dDither, states.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, r->stream) != cudaSuccess ||
+            cudaStreamSynchronize(r->stream) != cudaSuccess) {
+            set_error("tb200_finish: dither table upload failed");
+            return -1;
+        }
+        r->stats.h2dBytes += n * sizeof(uint2);
+        r->ditherReady = true;
+    }
+    FinishParams F;
+    F.accum = r->boundAccum ? r->boundAccum : r->dAccum;
+    F.numPixels = (int)n;
+    F.exposure = exposure;
+    F.filtered = filtered ? r->dFiltered : nullptr;
+    F.rgb8 = rgb8 ? r->dRgb8 : nullptr;
+    F.ditherState = r->dDither;
+    unsigned long long launches = 0;
+    cudaEventRecord(r->evStart, r->stream);
+    launch_finish(F, r->stream, &launches);
+    cudaEventRecord(r->evStop, r->stream);
+    r->stats.kernelLaunches += launches;
+    bool ok = cudaGetLastError() == cudaSuccess;
+    if (ok && filtered) {
+        ok = cudaMemcpyAsync(filtered, r->dFiltered, n * sizeof(float4), cudaMemcpyDeviceToHost, r->stream) == cudaSuccess;
+        r->stats.d2hBytes += n * sizeof(float4);
+    }
+    if (ok && rgb8) {
+        ok = cudaMemcpyAsync(rgb8, r->dRgb8, n * 3, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess;
+        r->stats.d2hBytes += n * 3;
+    }
+    ok = ok && cudaStreamSynchronize(r->stream) == cudaSuccess;
+    if (!ok) {
+        set_error(std::string("tb200_finish: ") + cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, r->evStart, r->evStop);
+    r->stats.gpuMs = ms;
+    return 0;
 }
 
 int tb200_trace_frame(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int frame,

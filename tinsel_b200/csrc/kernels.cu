@@ -148,4 +148,85 @@ void launch_normals(const LaunchParams& p, cudaStream_t stream, unsigned long lo
 // ------------------------------------------------------------------------------------------------
 // Wavefront pipeline: see wavefront2.cuh
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Display/finish step: exposure / weight normalisation, filmic tone map, sRGB, 8-bit with the PNG
+// writer's dither.  One thread = four consecutive pixels, so that the 8-bit output leaves as three
+// 32-bit words per thread; 64 B read + 64 B (+12 B) written per thread, nothing re-read.
+// ------------------------------------------------------------------------------------------------
+static __device__ __noinline__ float tb_powf(float x, float y) { return tbm_powf(x, y); }
+
+// ToneMap (util.h:25-42, filmic branch) followed by LinearToSrgb (maths.h:1545-1549), one channel
+TB_DEV float finish_channel(float t)
+{
+    const float b = t - 0.004f;
+    const float x = (0.0f < b) ? b : 0.0f;                       // Max(Vec3(0), texColor - Vec3(0.004))
+    const float num = x * (6.2f * x + 0.5f);
+    const float den = x * (6.2f * x + 1.7f) + 0.06f;             // Vec3(0.06): the double literal narrows to float
+    const float ret = num / den;
+    const float lin = tb_powf(ret, 2.2f);                        // SrgbToLinear
+    return tb_powf(lin, 1.0f / 2.2f);                            // LinearToSrgb, kInvGamma = 1.0f/2.2f
+}
+
+// Quantize(c*255.0 + Randf() + Randf() - 0.5f), png.cpp:324-343: the sum is formed in double
+// (255.0 is a double literal), narrowed to float at the call, clamped with Min(Max(x,0),255)
+// (maths.h:55-65: a NaN ends up as 255) and truncated.
+TB_DEV unsigned int finish_quantize(float c, Rng& rng)
+{
+    const float r1 = rng_float(rng);
+    const float r2 = rng_float(rng);
+    const double v = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn((double)c, 255.0), (double)r1), (double)r2), (double)0.5f);
+    float x = (float)v;
+    x = (x < 0.0f) ? 0.0f : x;
+    x = (x < 255.0f) ? x : 255.0f;
+    return (unsigned int)(unsigned char)x;
+}
+
+__global__ void __launch_bounds__(128) k_finish(FinishParams P)
+{
+    const int quad = blockIdx.x * blockDim.x + threadIdx.x;
+    const int first = quad * 4;
+    if (first >= P.numPixels) return;
+    unsigned int bytes[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = first + k;
+        float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (i < P.numPixels) {
+            const float4 p = __ldcs(&P.accum[i]);
+            const float s = P.exposure / p.w;                    // main.cpp:267
+            f.x = finish_channel(p.x * s);
+            f.y = finish_channel(p.y * s);
+            f.z = finish_channel(p.z * s);
+            f.w = 0.0f;                                          // ToneMap builds Color(retColor, 0.0f)
+            if (P.filtered) __stcs(&P.filtered[i], f);
+            if (P.rgb8) {
+                const uint2 st = __ldg(&P.ditherState[i]);
+                Rng rng;
+                rng.s1 = st.x;
+                rng.s2 = st.y;
+                bytes[k * 3 + 0] = finish_quantize(f.x, rng);
+                bytes[k * 3 + 1] = finish_quantize(f.y, rng);
+                bytes[k * 3 + 2] = finish_quantize(f.z, rng);
+            }
+        } else {
+            bytes[k * 3 + 0] = bytes[k * 3 + 1] = bytes[k * 3 + 2] = 0u;
+        }
+    }
+    if (P.rgb8) {
+        // the buffer is allocated in multiples of 12 bytes, so the last thread may write its padding
+        unsigned int* out = (unsigned int*)P.rgb8 + quad * 3;
+#pragma unroll
+        for (int w = 0; w < 3; ++w)
+            out[w] = bytes[w * 4] | (bytes[w * 4 + 1] << 8) | (bytes[w * 4 + 2] << 16) | (bytes[w * 4 + 3] << 24);
+    }
+}
+
+void launch_finish(const FinishParams& p, cudaStream_t stream, unsigned long long* launchCount)
+{
+    if (p.numPixels <= 0) return;
+    const int quads = (p.numPixels + 3) / 4;
+    k_finish<<<(quads + 127) / 128, 128, 0, stream>>>(p);
+    if (launchCount) ++*launchCount;
+}
+
 #include "wavefront2.cuh"

@@ -42,3 +42,14 @@ void launch_mega(const LaunchParams& p, cudaStream_t stream, unsigned long long*
 void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount);
 // eNormals mode (render.cpp:494-515)
 void launch_normals(const LaunchParams& p, cudaStream_t stream, unsigned long long* launchCount);
+
+// Display/finish step (src/main.cpp:258-271, src/png.cpp:329-343), see tb200_finish.
+struct FinishParams {
+    const float4* accum;      // width*height running sums
+    int numPixels;
+    float exposure;
+    float4* filtered;         // device, or nullptr
+    unsigned char* rgb8;      // device (numPixels*3 bytes, allocated in multiples of 12), or nullptr
+    const uint2* ditherState; // WritePng's Random state in front of each pixel's six draws (when rgb8)
+};
+void launch_finish(const FinishParams& p, cudaStream_t stream, unsigned long long* launchCount);

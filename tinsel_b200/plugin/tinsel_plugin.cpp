@@ -18,6 +18,7 @@
 #include "render.h"   // the reference's src/render.h
 
 #include "tinsel_b200.h"
+#include "tinsel_b200_plugin.h"
 
 static_assert(sizeof(BVHNode) == sizeof(tb200_bvh_node), "BVHNode layout (bvh.h:9-21)");
 static_assert(sizeof(Color) == 16 && sizeof(Vec3) == 12, "vector layouts (maths.h)");
@@ -142,6 +143,31 @@ struct GpuWavefrontRenderer : public Renderer {
 
 Renderer* CreateGpuWavefrontRenderer(const Scene* s) { return new GpuWavefrontRenderer(s); }
 
+// Optional fast paths (tinsel_b200_plugin.h) for a host that wants fewer read-backs than the
+// Renderer interface allows; both return false -- and do nothing -- for any other Renderer.
+bool TinselB200RenderN(Renderer* r, const Camera& c, const Options& options, int n, Color* output)
+{
+    GpuWavefrontRenderer* g = dynamic_cast<GpuWavefrontRenderer*>(r);
+    if (!g || !g->impl) return false;
+    if (tb200_render_n(g->impl, reinterpret_cast<const tb200_camera*>(&c), reinterpret_cast<const tb200_options*>(&options), n,
+                       reinterpret_cast<float*>(output)) != 0) {
+        fprintf(stderr, "TinselB200RenderN: %s\n", tb200_last_error());
+        return false;
+    }
+    return true;
+}
+
+bool TinselB200Finish(Renderer* r, const Options& options, Color* filtered, unsigned char* rgb8)
+{
+    GpuWavefrontRenderer* g = dynamic_cast<GpuWavefrontRenderer*>(r);
+    if (!g || !g->impl) return false;
+    if (tb200_finish(g->impl, options.exposure, options.limit, reinterpret_cast<float*>(filtered), rgb8) != 0) {
+        fprintf(stderr, "TinselB200Finish: %s\n", tb200_last_error());
+        return false;
+    }
+    return true;
+}
+
 // C shim so that tests can drive the C++ factory through ctypes: Create -> Init -> spp x Render -> delete.
 extern "C" int tb200_plugin_render(const void* scene, const void* camera, const void* options, int spp, float* output)
 {
@@ -153,4 +179,17 @@ extern "C" int tb200_plugin_render(const void* scene, const void* camera, const 
     const int rc = (err && err[0]) ? -1 : 0;
     delete r;
     return rc;
+}
+
+// Same, through the fast paths: Create -> Init -> RenderN(spp) -> Finish -> delete.
+extern "C" int tb200_plugin_present(const void* scene, const void* camera, const void* options, int spp, float* output,
+                                    float* filtered, unsigned char* rgb8)
+{
+    const Options& o = *static_cast<const Options*>(options);
+    Renderer* r = CreateGpuWavefrontRenderer(static_cast<const Scene*>(scene));
+    r->Init(o.width, o.height);
+    bool ok = TinselB200RenderN(r, *static_cast<const Camera*>(camera), o, spp, reinterpret_cast<Color*>(output));
+    ok = ok && TinselB200Finish(r, o, reinterpret_cast<Color*>(filtered), rgb8);
+    delete r;
+    return ok ? 0 : -1;
 }

@@ -175,9 +175,48 @@ def kat_fixtures():
     print("wrote kats.npz")
 
 
+def finish_inputs():
+    """Accumulator values for the finish-step fixtures: a rendered image plus adversarial sums
+    (zero weight -> inf/NaN scale, negative, huge, denormal, values around the 0.004 toe)."""
+    g = np.load(os.path.join(GOLD, "scene_cornell.npz"))
+    img = g["accum_4spp"].astype(np.float32)                    # 64x64x4
+    rng = np.random.RandomState(11)
+    adv = np.zeros((16, 64, 4), np.float32)
+    adv[..., 3] = rng.uniform(0.5, 6.0, adv.shape[:2])
+    adv[..., :3] = rng.uniform(0.0, 1.0, adv.shape[:2] + (3,)) ** 4 * adv[..., 3:4] * rng.choice([0.01, 0.3, 1.0, 8.0, 200.0], adv.shape[:2] + (1,))
+    adv[0, :8] = 0.0                                            # w == 0: exposure / 0 = inf, 0 * inf = NaN
+    adv[0, 8:16, :3] = 1.0
+    adv[0, 8:16, 3] = 0.0                                       # positive sums over zero weight: inf
+    adv[1, :8, :3] = -0.5                                       # negative radiance sums
+    adv[1, 8:16, :3] = 1e30
+    adv[1, 16:24, :3] = 1e-42                                   # denormal
+    adv[1, 24:32, :3] = np.float32(0.004) * adv[1, 24:32, 3:4]  # the toe of the filmic curve
+    adv[1, 32:40, 0] = np.nan
+    adv[1, 40:48, 3] = -1.0                                     # negative weight
+    return np.concatenate([img, adv], axis=0)                  # 80 x 64 x 4
+
+
+def finish_fixtures():
+    import tempfile
+    pixels = finish_inputs()
+    data = {"pixels": pixels, "exposures": np.array([1.0, 0.25, 3.5], np.float32)}
+    with tempfile.TemporaryDirectory() as tmp:
+        for k, e in enumerate(data["exposures"]):
+            f = refdrv.ref_finish(pixels, float(e))
+            data["filtered_%d" % k] = f
+            data["rgb8_%d" % k] = refdrv.ref_png_bytes(f, os.path.join(tmp, "f%d.png" % k))
+    np.savez_compressed(os.path.join(GOLD, "finish.npz"), **data)
+    print("wrote finish.npz")
+
+
 if __name__ == "__main__":
     # python tools/make_golden.py [scene ...]: no arguments regenerates everything
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ["finish"]:
+        finish_fixtures()
+        sys.exit(0)
     if len(sys.argv) == 1:
         kat_fixtures()
     scene_fixtures(sys.argv[1:])
+    if len(sys.argv) == 1:
+        finish_fixtures()
