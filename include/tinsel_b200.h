@@ -219,6 +219,15 @@ int tb200_render_n(tb200_renderer* r, const tb200_camera* camera, const tb200_op
  * include/tb200_detmath.h.  Returns 0 on success. */
 int tb200_finish(tb200_renderer* r, float exposure, float limit, float* filtered, unsigned char* rgb8);
 
+/* NonLocalMeansFilter(g_filtered, g_exposed, width, height, falloff, radius) of src/nlm.cpp:36-73
+ * (called from src/main.cpp:273-277 on the finished image when the viewer's denoise toggle is on),
+ * on the device, applied to the image the last tb200_finish produced (which stays resident):
+ * box means over the clamped (2*radius+1)^2 window (AverageFilter, nlm.cpp:4-34), then per pixel
+ * sum in[q]*w / sum w with w = expf(-falloff * |mean[p]-mean[q]|^2) over the same window, summed in
+ * the reference's order (columns outer, rows inner).  `out` is HOST memory, width*height*4 floats.
+ * Returns 0 on success, -1 if tb200_finish has not run since the last tb200_init. */
+int tb200_nlm(tb200_renderer* r, float falloff, int radius, float* out);
+
 /* Per-sample radiance probe used by the parity tests: traces frame `frame` only and writes,
  * for pixel p (row-major), radiance[3p..3p+2] = PathTrace() result and raster[2p..2p+1] =
  * jittered raster position, WITHOUT touching the accumulator.  Host pointers.  0 on success. */

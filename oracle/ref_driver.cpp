@@ -36,6 +36,7 @@
 #include "render.cpp"  // the reference's src/render.cpp (via -I/root/reference/src)
 #include "loader.h"
 #include "png.h"
+#include "nlm.h"
 
 #include "tinsel_b200.h"
 
@@ -401,6 +402,12 @@ void ref_finish(const float* pixels, int numPixels, float exposure, float limit,
 void ref_write_png(const float* filtered, int width, int height, const char* path)
 {
     WritePng((const Color*)filtered, width, height, path);
+}
+
+// The reference's own denoiser (src/nlm.cpp:36-73), as src/main.cpp:275 calls it.
+void ref_nlm(const float* in, float* out, int width, int height, float falloff, int radius)
+{
+    NonLocalMeansFilter((const Color*)in, (Color*)out, width, height, falloff, radius);
 }
 
 // One frame, no filtering: radiance[3p..] = PathTrace result, raster[2p..] = (x,y) of pixel p.

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <thread>
 #include <vector>
+#include <algorithm>
 
 #include "tb200_detmath.h"
 #include "tinsel_b200.h"
@@ -1120,6 +1121,48 @@ void oracle_quantize(const float* filtered, int numPixels, unsigned char* rgb8)
             x = (x < 0.0f) ? 0.0f : x;
             x = (x < 255.0f) ? x : 255.0f;
             rgb8[i * 3 + c] = (unsigned char)x;
+        }
+}
+
+// ---- non-local means, src/nlm.cpp ------------------------------------------------
+// AverageFilter (nlm.cpp:4-34) then NonLocalMeansFilter (nlm.cpp:36-73): window clamped to the
+// image, columns outer / rows inner, Color (4 floats) arithmetic, weight = expf(-falloff*LengthSq(dm)).
+void oracle_nlm(const float* in, float* out, int width, int height, float falloff, int radius)
+{
+    std::vector<float> means((size_t)width * height * 4);
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            int xlower = std::max(0, x - radius), xupper = std::min(width - 1, x + radius);
+            int ylower = std::max(0, y - radius), yupper = std::min(height - 1, y + radius);
+            int count = 0;
+            float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int fx = xlower; fx <= xupper; ++fx)
+                for (int fy = ylower; fy <= yupper; ++fy) {
+                    const float* p = in + ((size_t)fy * width + fx) * 4;
+                    for (int c = 0; c < 4; ++c) sum[c] = sum[c] + p[c];
+                    count += 1;
+                }
+            float inv = 1.0f / count;
+            for (int c = 0; c < 4; ++c) means[((size_t)y * width + x) * 4 + c] = sum[c] * inv;
+        }
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            int xlower = std::max(0, x - radius), xupper = std::min(width - 1, x + radius);
+            int ylower = std::max(0, y - radius), yupper = std::min(height - 1, y + radius);
+            float totalWeight = 0.0f;
+            float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            const float* mean = &means[((size_t)y * width + x) * 4];
+            for (int fx = xlower; fx <= xupper; ++fx)
+                for (int fy = ylower; fy <= yupper; ++fy) {
+                    const float* m = &means[((size_t)fy * width + fx) * 4];
+                    float dx = mean[0] - m[0], dy = mean[1] - m[1], dz = mean[2] - m[2], dw = mean[3] - m[3];
+                    float weight = tbm_expf(-falloff * (dx * dx + dy * dy + dz * dz + dw * dw));
+                    const float* p = in + ((size_t)fy * width + fx) * 4;
+                    for (int c = 0; c < 4; ++c) sum[c] = sum[c] + p[c] * weight;
+                    totalWeight += weight;
+                }
+            float inv = 1.0f / totalWeight;
+            for (int c = 0; c < 4; ++c) out[((size_t)y * width + x) * 4 + c] = sum[c] * inv;
         }
 }
 

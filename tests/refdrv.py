@@ -79,6 +79,7 @@ def load_ref(flavour="detmath"):
     lib.ref_primitive_sample.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, _f32p, _f32p, _f32p]
     lib.ref_finish.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
     lib.ref_write_png.argtypes = [_f32p, C.c_int, C.c_int, C.c_char_p]
+    lib.ref_nlm.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_int]
     _libs[flavour] = lib
     return lib
 
@@ -203,6 +204,7 @@ def load_port():
     lib.oracle_primitive_sample.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, _f32p, _f32p, _f32p]
     lib.oracle_finish.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
     lib.oracle_quantize.argtypes = [_f32p, C.c_int, C.POINTER(C.c_ubyte)]
+    lib.oracle_nlm.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_int]
     abi.declare_snapshot_api(lib)
     _port = lib
     return lib
@@ -286,4 +288,19 @@ def port_quantize(filtered):
     h, w = filtered.shape[:2]
     out = np.empty((h, w, 3), np.uint8)
     load_port().oracle_quantize(_fp(filtered), h * w, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return out
+
+
+def ref_nlm(image, falloff, radius, flavour="detmath"):
+    """The reference's NonLocalMeansFilter (src/nlm.cpp) over `image` (H,W,4)."""
+    image = np.ascontiguousarray(image, np.float32)
+    out = np.empty_like(image)
+    load_ref(flavour).ref_nlm(_fp(image), _fp(out), image.shape[1], image.shape[0], falloff, radius)
+    return out
+
+
+def port_nlm(image, falloff, radius):
+    image = np.ascontiguousarray(image, np.float32)
+    out = np.empty_like(image)
+    load_port().oracle_nlm(_fp(image), _fp(out), image.shape[1], image.shape[0], falloff, radius)
     return out

@@ -62,7 +62,58 @@ def test_literal_libm_agrees_to_one_ulp():
     assert np.allclose(a, b, rtol=4e-7, atol=1e-7)
 
 
+def test_port_nlm_matches_golden_and_reference():
+    """NonLocalMeansFilter (src/nlm.cpp:36-73): restatement vs golden vectors from the reference's own
+    compiled filter (radius 0, 1 = what main.cpp uses, 3), and vs the reference directly on a ragged image."""
+    g = np.load(GOLD)
+    img = g["filtered_0"][:64]
+    assert _same(refdrv.port_nlm(img, 200.0, 1), g["nlm_r1"])
+    assert _same(refdrv.port_nlm(img, 35.0, 3), g["nlm_r3"])
+    assert _same(refdrv.port_nlm(img, 200.0, 0), g["nlm_r0"])
+    assert _same(g["nlm_r0"][..., :3], img[..., :3])          # a 1x1 window returns the pixel itself (x*1/1)
+    if refdrv.have_ref("detmath"):
+        rng = np.random.RandomState(5)
+        im = rng.uniform(0.0, 1.0, (19, 7, 4)).astype(np.float32)
+        for radius, falloff in ((1, 200.0), (2, 10.0), (9, 1.0)):   # radius 9 > the image width: fully clamped windows
+            assert _same(refdrv.port_nlm(im, falloff, radius), refdrv.ref_nlm(im, falloff, radius))
+
+
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_nlm_bit_exact():
+    import torch
+    g = np.load(GOLD)
+    px = g["pixels"][:64]
+    h, w = px.shape[:2]
+    snap = tb.Snapshot(tb.scene_path("cornell"))
+    r = tb.Renderer(snap.scene)
+    r.Init(w, h)
+    with pytest.raises(tb.TinselB200Error):
+        r.nlm(200.0, 1)                                         # nothing finished yet
+    acc = torch.from_numpy(px.copy()).cuda()
+    r.bind_accumulator(acc.data_ptr())
+    f, _ = r.finish(1.0, 1.5, filtered=True, rgb8=False)
+    assert _same(f, g["filtered_0"][:64])
+    assert _same(r.nlm(200.0, 1), g["nlm_r1"])
+    assert _same(r.nlm(35.0, 3), g["nlm_r3"])
+    assert _same(r.nlm(200.0, 0), g["nlm_r0"])
+    r.close()
+    snap.close()
+    # a rendered, ragged-size image with the 8-bit-only finish in front (the float image stays on the device)
+    snap = tb.Snapshot(tb.scene_path("veach"))
+    cam, opt = snap.camera, snap.options
+    opt.width, opt.height = 203, 77
+    r = tb.Renderer(snap.scene)
+    r.Init(opt.width, opt.height)
+    out = np.zeros((opt.height, opt.width, 4), np.float32)
+    r.render_n(cam, opt, 4, out)
+    r.finish(float(opt.exposure), float(opt.limit), filtered=False, rgb8=True)
+    want = refdrv.port_nlm(refdrv.port_finish(out, float(opt.exposure)), 200.0, 2)
+    assert _same(r.nlm(200.0, 2), want)
+    r.close()
+    snap.close()
+
+
 @pytest.mark.gpu
 def test_gpu_finish_bit_exact_on_golden_accumulators():
     import torch

@@ -60,6 +60,8 @@ def load_library():
     lib.tb200_render_n.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), C.c_int, f32p]
     lib.tb200_finish.restype = C.c_int
     lib.tb200_finish.argtypes = [C.c_void_p, C.c_float, C.c_float, f32p, C.POINTER(C.c_ubyte)]
+    lib.tb200_nlm.restype = C.c_int
+    lib.tb200_nlm.argtypes = [C.c_void_p, C.c_float, C.c_int, f32p]
     lib.tb200_trace_frame.restype = C.c_int
     lib.tb200_trace_frame.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Options), C.c_int, f32p, f32p]
     lib.tb200_set_frame.restype = None
@@ -182,6 +184,12 @@ class Renderer:
         self._check(self.lib.tb200_finish(self.h, exposure, limit, _fp(f) if filtered else None,
                                           b.ctypes.data_as(C.POINTER(C.c_ubyte)) if rgb8 else None), "tb200_finish")
         return f, b
+
+    def nlm(self, falloff, radius):
+        """NonLocalMeansFilter (src/nlm.cpp:36-73) of the image the last finish() produced: (H,W,4) float32."""
+        out = np.empty((self.height, self.width, 4), np.float32)
+        self._check(self.lib.tb200_nlm(self.h, falloff, radius, _fp(out)), "tb200_nlm")
+        return out
 
     def device_accumulator_ptr(self):
         return self.lib.tb200_device_accumulator(self.h)

@@ -160,6 +160,7 @@ EXPORTS = [
     "tb200_read_accumulator",
     "tb200_render_n",
     "tb200_finish",
+    "tb200_nlm",
     "tb200_trace_frame",
     "tb200_set_frame",
     "tb200_get_stats",

@@ -279,8 +279,11 @@ struct tb200_renderer {
     float4* dFiltered = nullptr;
     unsigned char* dRgb8 = nullptr;
     uint2* dDither = nullptr;
-    int finishWidth = 0, finishHeight = 0;   // size the three buffers above were made for
+    float4* dMeans = nullptr;                // tb200_nlm scratch + output
+    float4* dDenoised = nullptr;
+    int finishWidth = 0, finishHeight = 0;   // size the buffers above were made for
     bool ditherReady = false;
+    bool filteredValid = false;              // dFiltered holds the image of a tb200_finish since the last tb200_init
 
     // streamed read-back (tb200_render): band counters on the device, completion flags in mapped
     // host memory, a private copy stream
@@ -326,11 +329,15 @@ void free_device(tb200_renderer* r)
     cudaFree(r->dFiltered);
     cudaFree(r->dRgb8);
     cudaFree(r->dDither);
+    cudaFree(r->dMeans);
+    cudaFree(r->dDenoised);
     r->dFiltered = nullptr;
     r->dRgb8 = nullptr;
     r->dDither = nullptr;
+    r->dMeans = r->dDenoised = nullptr;
     r->finishWidth = r->finishHeight = 0;
     r->ditherReady = false;
+    r->filteredValid = false;
     if (r->hBandFlags) cudaFreeHost((void*)r->hBandFlags);
     r->hBandFlags = nullptr;
     r->dBandFlags = nullptr;
@@ -748,6 +755,7 @@ int tb200_init(tb200_renderer* r, int width, int height)
     r->frame = 0;
     r->stats.frames = 0;
     r->boundAccum = nullptr;
+    r->filteredValid = false;
     return 0;
 }
 
@@ -928,10 +936,14 @@ int tb200_finish(tb200_renderer* r, float exposure, float limit, float* filtered
         cudaFree(r->dFiltered);
         cudaFree(r->dRgb8);
         cudaFree(r->dDither);
+        cudaFree(r->dMeans);
+        cudaFree(r->dDenoised);
         r->dFiltered = nullptr;
         r->dRgb8 = nullptr;
         r->dDither = nullptr;
+        r->dMeans = r->dDenoised = nullptr;
         r->ditherReady = false;
+        r->filteredValid = false;
         r->finishWidth = r->finishHeight = 0;
         if (cudaMalloc((void**)&r->dFiltered, n * sizeof(float4)) != cudaSuccess ||
             cudaMalloc((void**)&r->dRgb8, rgbBytes) != cudaSuccess ||
@@ -968,7 +980,7 @@ int tb200_finish(tb200_renderer* r, float exposure, float limit, float* filtered
     F.accum = r->boundAccum ? r->boundAccum : r->dAccum;
     F.numPixels = (int)n;
     F.exposure = exposure;
-    F.filtered = filtered ? r->dFiltered : nullptr;
+    F.filtered = r->dFiltered;   // always kept on the device: tb200_nlm reads it
     F.rgb8 = rgb8 ? r->dRgb8 : nullptr;
     F.ditherState = r->dDither;
     unsigned long long launches = 0;
@@ -990,6 +1002,52 @@ int tb200_finish(tb200_renderer* r, float exposure, float limit, float* filtered
         set_error(std::string("tb200_finish: ") + cudaGetErrorString(cudaGetLastError()));
         return -1;
     }
+    r->filteredValid = true;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, r->evStart, r->evStop);
+    r->stats.gpuMs = ms;
+    return 0;
+}
+
+int tb200_nlm(tb200_renderer* r, float falloff, int radius, float* out)
+{
+    if (!r || !out || radius < 0) {
+        set_error("tb200_nlm: bad argument");
+        return -1;
+    }
+    if (!r->filteredValid || r->finishWidth != r->width || r->finishHeight != r->height) {
+        set_error("tb200_nlm: tb200_finish has not produced an image since the last tb200_init");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    const size_t n = size_t(r->width) * r->height;
+    if (!r->dMeans) {
+        if (cudaMalloc((void**)&r->dMeans, n * sizeof(float4)) != cudaSuccess ||
+            cudaMalloc((void**)&r->dDenoised, n * sizeof(float4)) != cudaSuccess) {
+            set_error("tb200_nlm: buffer allocation failed");
+            return -1;
+        }
+    }
+    NlmParams N;
+    N.in = r->dFiltered;
+    N.means = r->dMeans;
+    N.out = r->dDenoised;
+    N.width = r->width;
+    N.height = r->height;
+    N.radius = radius;
+    N.falloff = falloff;
+    unsigned long long launches = 0;
+    cudaEventRecord(r->evStart, r->stream);
+    launch_nlm(N, r->stream, &launches);
+    cudaEventRecord(r->evStop, r->stream);
+    r->stats.kernelLaunches += launches;
+    if (cudaGetLastError() != cudaSuccess ||
+        cudaMemcpyAsync(out, r->dDenoised, n * sizeof(float4), cudaMemcpyDeviceToHost, r->stream) != cudaSuccess ||
+        cudaStreamSynchronize(r->stream) != cudaSuccess) {
+        set_error(std::string("tb200_nlm: ") + cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    r->stats.d2hBytes += n * sizeof(float4);
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, r->evStart, r->evStop);
     r->stats.gpuMs = ms;

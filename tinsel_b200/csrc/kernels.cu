@@ -229,4 +229,60 @@ void launch_finish(const FinishParams& p, cudaStream_t stream, unsigned long lon
     if (launchCount) ++*launchCount;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Non-local means on the finished image (src/nlm.cpp).  One thread per pixel, 32x8 pixel blocks so
+// that the window taps of a block overlap in L1; sums run in the reference's order (columns outer,
+// rows inner) because fp32 addition order is part of the result.
+// ------------------------------------------------------------------------------------------------
+TB_DEV float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+TB_DEV float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+// AverageFilter, nlm.cpp:4-34
+__global__ void __launch_bounds__(256) k_nlm_mean(NlmParams P)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.width || y >= P.height) return;
+    const int xlower = max(0, x - P.radius), xupper = min(P.width - 1, x + P.radius);
+    const int ylower = max(0, y - P.radius), yupper = min(P.height - 1, y + P.radius);
+    int count = 0;
+    float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int fx = xlower; fx <= xupper; ++fx)
+        for (int fy = ylower; fy <= yupper; ++fy) {
+            sum = f4_add(sum, __ldg(&P.in[fy * P.width + fx]));
+            count += 1;
+        }
+    P.means[y * P.width + x] = f4_scale(sum, 1.0f / (float)count);
+}
+
+// NonLocalMeansFilter, nlm.cpp:36-73
+__global__ void __launch_bounds__(256) k_nlm(NlmParams P)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.width || y >= P.height) return;
+    const int xlower = max(0, x - P.radius), xupper = min(P.width - 1, x + P.radius);
+    const int ylower = max(0, y - P.radius), yupper = min(P.height - 1, y + P.radius);
+    float totalWeight = 0.0f;
+    float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float4 mean = P.means[y * P.width + x];
+    for (int fx = xlower; fx <= xupper; ++fx)
+        for (int fy = ylower; fy <= yupper; ++fy) {
+            const float4 m = P.means[fy * P.width + fx];
+            const float dx = mean.x - m.x, dy = mean.y - m.y, dz = mean.z - m.z, dw = mean.w - m.w;
+            const float lsq = dx * dx + dy * dy + dz * dz + dw * dw;       // LengthSq(Vec4), maths.h:331-332
+            const float weight = tb_expf(-P.falloff * lsq);
+            sum = f4_add(sum, f4_scale(__ldg(&P.in[fy * P.width + fx]), weight));
+            totalWeight += weight;
+        }
+    __stcs(&P.out[y * P.width + x], f4_scale(sum, 1.0f / totalWeight));
+}
+
+void launch_nlm(const NlmParams& p, cudaStream_t stream, unsigned long long* launchCount)
+{
+    if (p.width <= 0 || p.height <= 0) return;
+    const dim3 grid((p.width + 31) / 32, (p.height + 7) / 8);
+    k_nlm_mean<<<grid, 256, 0, stream>>>(p);
+    k_nlm<<<grid, 256, 0, stream>>>(p);
+    if (launchCount) *launchCount += 2;
+}
+
 #include "wavefront2.cuh"

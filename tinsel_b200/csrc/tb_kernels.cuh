@@ -53,3 +53,13 @@ struct FinishParams {
     const uint2* ditherState; // WritePng's Random state in front of each pixel's six draws (when rgb8)
 };
 void launch_finish(const FinishParams& p, cudaStream_t stream, unsigned long long* launchCount);
+
+// NonLocalMeansFilter (src/nlm.cpp:4-73) on the finished image; see tb200_nlm.
+struct NlmParams {
+    const float4* in;     // finished image (k_finish output)
+    float4* means;        // scratch: AverageFilter output
+    float4* out;
+    int width, height, radius;
+    float falloff;
+};
+void launch_nlm(const NlmParams& p, cudaStream_t stream, unsigned long long* launchCount);

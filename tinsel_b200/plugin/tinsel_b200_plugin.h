@@ -16,3 +16,7 @@ bool TinselB200RenderN(Renderer* r, const Camera& camera, const Options& options
 // and/or the 8-bit RGB buffer WritePng would build from it (src/png.cpp:329-343, same dither).
 // Either pointer may be null.
 bool TinselB200Finish(Renderer* r, const Options& options, Color* filtered, unsigned char* rgb8);
+
+// NonLocalMeansFilter(g_filtered, g_exposed, w, h, falloff, radius) of src/main.cpp:273-277 on the
+// device, applied to the image the last TinselB200Finish produced (src/nlm.cpp:36-73, same sums).
+bool TinselB200Nlm(Renderer* r, float falloff, int radius, Color* out);

@@ -181,6 +181,17 @@ extern "C" int tb200_plugin_render(const void* scene, const void* camera, const 
     return rc;
 }
 
+bool TinselB200Nlm(Renderer* r, float falloff, int radius, Color* out)
+{
+    GpuWavefrontRenderer* g = dynamic_cast<GpuWavefrontRenderer*>(r);
+    if (!g || !g->impl) return false;
+    if (tb200_nlm(g->impl, falloff, radius, reinterpret_cast<float*>(out)) != 0) {
+        fprintf(stderr, "TinselB200Nlm: %s\n", tb200_last_error());
+        return false;
+    }
+    return true;
+}
+
 // Same, through the fast paths: Create -> Init -> RenderN(spp) -> Finish -> delete.
 extern "C" int tb200_plugin_present(const void* scene, const void* camera, const void* options, int spp, float* output,
                                     float* filtered, unsigned char* rgb8)

@@ -67,5 +67,15 @@ res["k_finish_GBps"] = w * h * (16 + 16 + 3 + 8) / (res["k_finish_ms"] * 1e-3) /
 t0 = time.perf_counter()
 f = refdrv.port_finish(out, 1.0)
 res["host_finish_1thread_ms"] = (time.perf_counter() - t0) * 1e3
+r.finish(1.0, 1.5, filtered=False, rgb8=False)
+ks = []
+for _ in range(5):
+    r.nlm(200.0, 1)
+    ks.append(r.stats().gpuMs)
+res["k_nlm_r1_ms"] = sorted(ks)[2]
+res["nlm_r1_call_ms"] = timed(lambda: r.nlm(200.0, 1))
+t0 = time.perf_counter()
+refdrv.port_nlm(f, 200.0, 1)
+res["host_nlm_r1_1thread_ms"] = (time.perf_counter() - t0) * 1e3
 print(scene, w, h, res)
 r.close()

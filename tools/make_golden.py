@@ -205,6 +205,11 @@ def finish_fixtures():
             f = refdrv.ref_finish(pixels, float(e))
             data["filtered_%d" % k] = f
             data["rgb8_%d" % k] = refdrv.ref_png_bytes(f, os.path.join(tmp, "f%d.png" % k))
+        # NonLocalMeansFilter on the finished image (src/main.cpp:275: falloff 200, radius 1), plus a wider window
+        img = data["filtered_0"][:64]
+        data["nlm_r1"] = refdrv.ref_nlm(img, 200.0, 1)
+        data["nlm_r3"] = refdrv.ref_nlm(img, 35.0, 3)
+        data["nlm_r0"] = refdrv.ref_nlm(img, 200.0, 0)
     np.savez_compressed(os.path.join(GOLD, "finish.npz"), **data)
     print("wrote finish.npz")
 
