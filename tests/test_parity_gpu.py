@@ -210,11 +210,15 @@ def test_max_depth_edge_cases(depth, pipeline):
     snap.close()
 
 
+@pytest.mark.parametrize("cta", ["512", "768"])
 @pytest.mark.parametrize("sched", ["hard", "free"])
-def test_both_scheduling_modes_bit_exact(sched):
+def test_both_scheduling_modes_bit_exact(sched, cta):
+    """Every scheduling mode x CTA size of the wavefront kernel (the per-scene heuristics of
+    api.cu build_scene pick one of them) produces the same bits."""
     os.environ["TINSEL_B200_SCHED"] = sched
+    os.environ["TINSEL_B200_CTA"] = cta
     try:
-        for name in ("veach", "meshlight", "many"):
+        for name in ("veach", "meshlight", "many", "envmini"):
             snap, cam, opt, ref, r = _setup(name, "wavefront")
             rad, _ = r.trace_frame(cam, opt, 3)
             rrad, _ = ref.trace_frame(3, nthreads=8)
@@ -224,6 +228,7 @@ def test_both_scheduling_modes_bit_exact(sched):
             snap.close()
     finally:
         os.environ.pop("TINSEL_B200_SCHED", None)
+        os.environ.pop("TINSEL_B200_CTA", None)
 
 
 def test_box_filter_and_clamp():

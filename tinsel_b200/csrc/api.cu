@@ -301,6 +301,7 @@ struct tb200_renderer {
 
     int pipeline = 2;             // 0 = mega (validation), 2 = wavefront (product)
     int hardPhases = 1;           // wavefront scheduling mode (see wavefront2.cuh)
+    int wideCta = 0;              // 768-thread CTAs for deep mesh BVHs (see wavefront2.cuh)
     tb200_stats stats;
 };
 
@@ -410,6 +411,12 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
         const char* sched = getenv("TINSEL_B200_SCHED");
         if (sched && strcmp(sched, "hard") == 0) r->hardPhases = 1;
         if (sched && strcmp(sched, "free") == 0) r->hardPhases = 0;
+        // CTA size: deep mesh BVHs make traversal latency bound (L2 hits), which more warps hide; on
+        // scenes held in shared memory more warps only thrash the instruction cache.  TINSEL_B200_CTA=512|768.
+        r->wideCta = (!r->hardPhases && maxTris > 4096) ? 1 : 0;
+        const char* cta = getenv("TINSEL_B200_CTA");
+        if (cta && atoi(cta) == 768) r->wideCta = 1;
+        if (cta && atoi(cta) == 512) r->wideCta = 0;
     }
 
     // primitives
@@ -519,6 +526,7 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     P->accum = r->boundAccum ? r->boundAccum : r->dAccum;
     P->sampleCounter = r->dCounter;
     P->hardPhases = r->hardPhases;
+    P->wideCta = r->wideCta;
     P->firstRow = 0;
     P->numRows = o->height;
     P->shard = r->shard;

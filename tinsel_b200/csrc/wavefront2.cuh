@@ -33,6 +33,9 @@
 #ifndef TB_WF2_THREADS
 #define TB_WF2_THREADS 512
 #endif
+#ifndef TB_WF2_THREADS_WIDE
+#define TB_WF2_THREADS_WIDE 768
+#endif
 #ifndef TB_WF2_PATHS
 #define TB_WF2_PATHS 1024      // must be a power of two <= 1024 (10-bit slot ids in the queue cells)
 #endif
@@ -276,7 +279,11 @@ TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf
     return true;
 }
 
-__global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(LaunchParams P, unsigned long long total)
+// THREADS: 512 (16 warps, up to 128 registers) for scenes held in shared memory, where more warps
+// only add instruction-cache pressure; 768 (24 warps, 80 registers) for scenes with deep mesh BVHs,
+// whose traversal is latency bound on L2 and pays for the extra warps (LaunchParams::wideCta).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(LaunchParams P, unsigned long long total)
 {
     extern __shared__ __align__(16) unsigned char wf_smem_raw[];
     Wf2Shared& S = *reinterpret_cast<Wf2Shared*>(wf_smem_raw);
@@ -288,26 +295,26 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
         const int words = sc.numPrims * (int)(sizeof(DPrim) / 4);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.prims);
         uint32_t* dst = reinterpret_cast<uint32_t*>(S.prims);
-        for (int i = tid; i < words; i += TB_WF2_THREADS) dst[i] = src[i];
+        for (int i = tid; i < words; i += THREADS) dst[i] = src[i];
         sc.prims = S.prims;
     }
     if (sc.numPairs <= TB_WF2_MAX_PAIRS) {
         const int words = sc.numPairs * (int)(sizeof(BvhPair) / 4);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.pairs);
         uint32_t* dst = reinterpret_cast<uint32_t*>(S.pairs);
-        for (int i = tid; i < words; i += TB_WF2_THREADS) dst[i] = src[i];
+        for (int i = tid; i < words; i += THREADS) dst[i] = src[i];
         sc.pairs = S.pairs;
     }
     if (sc.numFlat > 0 && sc.numFlat <= 32) {
         const int words = sc.numFlat * (int)(sizeof(ProgOp) / 4);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.flat);
         uint32_t* dst = reinterpret_cast<uint32_t*>(S.flat);
-        for (int i = tid; i < words; i += TB_WF2_THREADS) dst[i] = src[i];
+        for (int i = tid; i < words; i += THREADS) dst[i] = src[i];
         sc.flat = S.flat;
     }
     // every slot starts in the R queue "finished with nothing to splat": stage R fills it with a
     // camera sample
-    for (int s = tid; s < TB_WF2_PATHS; s += TB_WF2_THREADS) {
+    for (int s = tid; s < TB_WF2_PATHS; s += THREADS) {
         S.ring[WF2_Q_R][s] = wf2_cell((unsigned)s, s);
         S.ring[WF2_Q_T][s] = 0;
         S.ring[WF2_Q_A][s] = 0;
@@ -622,27 +629,34 @@ __global__ void __launch_bounds__(TB_WF2_THREADS, TB_WF2_CTAS_PER_SM) k_wavefron
     }
 }
 
+template <int THREADS>
+static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long total)
+{
+    static bool configured = false;
+    static int ctasPerSM = 0;
+    if (!configured) {
+        cudaFuncSetAttribute(k_wavefront2<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wf2Shared));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_wavefront2<THREADS>, THREADS, sizeof(Wf2Shared)) != cudaSuccess ||
+            ctasPerSM < 1)
+            ctasPerSM = 1;
+        configured = true;
+    }
+    // TB_WF2_CTAS_PER_SM resident CTAs per SM; small jobs use fewer so that every CTA has a full slot array
+    const unsigned long long want = (total + TB_WF2_PATHS - 1) / TB_WF2_PATHS;
+    int grid = (numSMs > 0 ? numSMs : 148) * ctasPerSM;
+    if (want < (unsigned long long)grid) grid = (int)want;
+    if (grid < 1) grid = 1;
+    k_wavefront2<THREADS><<<grid, THREADS, sizeof(Wf2Shared), stream>>>(p, total);
+}
+
 void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
 {
     const unsigned long long total = p.samplesPerFrame * (unsigned long long)p.numFrames;
     if (total == 0ull) return;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_wavefront2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wf2Shared));
-        configured = true;
-    }
     cudaMemsetAsync(p.sampleCounter, 0, sizeof(unsigned long long), stream);
-    // TB_WF2_CTAS_PER_SM resident CTAs per SM; small jobs use fewer so that every CTA has a full slot array
-    unsigned long long want = (total + TB_WF2_PATHS - 1) / TB_WF2_PATHS;
-    static int ctasPerSM = 0;
-    if (ctasPerSM == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_wavefront2, TB_WF2_THREADS, sizeof(Wf2Shared)) != cudaSuccess ||
-            ctasPerSM < 1)
-            ctasPerSM = 1;
-    }
-    int grid = (numSMs > 0 ? numSMs : 148) * ctasPerSM;
-    if (want < (unsigned long long)grid) grid = (int)want;
-    if (grid < 1) grid = 1;
-    k_wavefront2<<<grid, TB_WF2_THREADS, sizeof(Wf2Shared), stream>>>(p, total);
+    if (p.wideCta)
+        launch_wavefront2_t<TB_WF2_THREADS_WIDE>(p, numSMs, stream, total);
+    else
+        launch_wavefront2_t<TB_WF2_THREADS>(p, numSMs, stream, total);
     if (launchCount) ++*launchCount;
 }
