@@ -211,14 +211,16 @@ def test_max_depth_edge_cases(depth, pipeline):
 
 
 @pytest.mark.parametrize("cta", ["512", "768"])
-@pytest.mark.parametrize("sched", ["hard", "free"])
+@pytest.mark.parametrize("sched", ["hard", "free", "split"])
 def test_both_scheduling_modes_bit_exact(sched, cta):
-    """Every scheduling mode x CTA size of the wavefront kernel (the per-scene heuristics of
-    api.cu build_scene pick one of them) produces the same bits."""
-    os.environ["TINSEL_B200_SCHED"] = sched
+    """Every scheduler variant x CTA size of the wavefront kernel (the per-scene heuristics of
+    api.cu build_scene pick one of them) produces the same bits: hard phases, free running, and
+    free running with the split trace queue forced on for every scene that has a mesh."""
+    os.environ["TINSEL_B200_SCHED"] = "free" if sched == "split" else sched
+    os.environ["TINSEL_B200_SPLIT"] = "1" if sched == "split" else "0"
     os.environ["TINSEL_B200_CTA"] = cta
     try:
-        for name in ("veach", "meshlight", "many", "envmini"):
+        for name in ("veach", "meshlight", "many", "envmini", "glass"):
             snap, cam, opt, ref, r = _setup(name, "wavefront")
             rad, _ = r.trace_frame(cam, opt, 3)
             rrad, _ = ref.trace_frame(3, nthreads=8)
@@ -228,6 +230,7 @@ def test_both_scheduling_modes_bit_exact(sched, cta):
             snap.close()
     finally:
         os.environ.pop("TINSEL_B200_SCHED", None)
+        os.environ.pop("TINSEL_B200_SPLIT", None)
         os.environ.pop("TINSEL_B200_CTA", None)
 
 

@@ -414,6 +414,30 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
         // CTA size: deep mesh BVHs make traversal latency bound (L2 hits), which more warps hide; on
         // scenes held in shared memory more warps only thrash the instruction cache.  TINSEL_B200_CTA=512|768.
         r->wideCta = (!r->hardPhases && maxTris > 4096) ? 1 : 0;
+        // Split trace queue: rays entering the largest mesh's world bounds are queued apart from the
+        // rest (scheduling only).  Bounds come from that primitive's leaf in the scene BVH.
+        r->scene.splitValid = 0;
+        const char* split = getenv("TINSEL_B200_SPLIT");   // 0: never, 1: whenever the scene has a mesh (tests)
+        if (maxTris > 4096 || (split && atoi(split) == 1)) {
+            int bigPrim = -1, bigTris = 0;
+            for (int i = 0; i < s->numPrimitives; ++i) {
+                const tb200_primitive& p = s->primitives[i];
+                if (p.type == TB200_MESH && p.mesh >= 0 && p.mesh < s->numMeshes && s->meshes[p.mesh].numIndices / 3 > bigTris) {
+                    bigTris = s->meshes[p.mesh].numIndices / 3;
+                    bigPrim = i;
+                }
+            }
+            for (int n = 0; n < s->numBvhNodes && bigPrim >= 0; ++n) {
+                const tb200_bvh_node& node = s->bvhNodes[n];
+                if ((node.right_leaf >> 31) != 0 && (int)node.left == bigPrim) {
+                    r->scene.splitLo = v3(node.lower[0], node.lower[1], node.lower[2]);
+                    r->scene.splitHi = v3(node.upper[0], node.upper[1], node.upper[2]);
+                    r->scene.splitValid = 1;
+                    break;
+                }
+            }
+        }
+        if (split && atoi(split) == 0) r->scene.splitValid = 0;
         const char* cta = getenv("TINSEL_B200_CTA");
         if (cta && atoi(cta) == 768) r->wideCta = 1;
         if (cta && atoi(cta) == 512) r->wideCta = 0;

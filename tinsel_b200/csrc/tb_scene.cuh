@@ -95,6 +95,12 @@ struct DScene {
     int numNee;               // shadow rays per surface hit: probe + sum(lightSamples)
     const struct ProgOp* flat;     // flat scene program (numFlat == 0: use the ordered walk)
     int numFlat;
+    // Scheduling hint only (never changes a result): world-space bounds of the scene's largest mesh
+    // when it is big enough for its BVH walk to dominate a ray's cost.  The wavefront kernel queues
+    // rays that enter this box separately from the rest, so that a warp's 32 rays either all walk
+    // the mesh or none does.
+    int splitValid;
+    V3 splitLo, splitHi;
 };
 
 struct Hit {

@@ -76,8 +76,8 @@ struct Wf2Shared {
     float lax[TB_WF2_PATHS], lay[TB_WF2_PATHS], laz[TB_WF2_PATHS];
     uint32_t cursor[TB_WF2_PATHS];    // slot | prim << 8 | sample << 20
     // stage queues: rings of lap-tagged slot ids
-    uint16_t ring[6][TB_WF2_PATHS];
-    unsigned int head[6], tail[6];
+    uint16_t ring[7][TB_WF2_PATHS];
+    unsigned int head[7], tail[7];
     unsigned int snap[5];             // hard-phase mode: the tail each stage of the current phase runs with
     int pref;                         // stage the warps currently prefer (soft phases, see the main loop)
     int live;                         // slots that still hold (or may still receive) a path
@@ -90,7 +90,10 @@ struct Wf2Shared {
 
 // stage queues.  T, A, B, R in the cyclic order of the free-running sweep; F0/F1 hold the freshly
 // regenerated camera rays in hard-phase mode (double-buffered: R fills one while T drains the other)
-enum { WF2_Q_T = 0, WF2_Q_A = 1, WF2_Q_B = 2, WF2_Q_R = 3, WF2_Q_F0 = 4, WF2_Q_F1 = 5 };
+// TM (free-running mode, scenes with DScene::splitValid): rays that enter the big mesh's box; same
+// stage code as T, but a chunk taken from TM walks the mesh with all of its lanes and a chunk taken
+// from T with none.
+enum { WF2_Q_T = 0, WF2_Q_A = 1, WF2_Q_B = 2, WF2_Q_R = 3, WF2_Q_F0 = 4, WF2_Q_F1 = 5, WF2_Q_TM = 6 };
 #define WF2_MASK (TB_WF2_PATHS - 1)
 #define WF2_LOG2_PATHS (TB_WF2_PATHS == 1024 ? 10 : TB_WF2_PATHS == 512 ? 9 : TB_WF2_PATHS == 256 ? 8 : 7)
 
@@ -117,6 +120,34 @@ TB_DEV void wf2_push(Wf2Shared& S, int q, bool flag, int slot)
         const unsigned int idx = base + (unsigned)__popc(m & ((1u << lane) - 1u));
         *(volatile uint16_t*)&S.ring[q][idx & WF2_MASK] = wf2_cell(idx, slot);
     }
+}
+
+// Push a slot whose pending ray is ready to be traced.  With `split` set the ray (extension ray, or
+// the shadow ray from the hit point) is classified against the big mesh's bounds first; the test
+// is a scheduling heuristic, so the unoffset hit point is good enough as the shadow-ray origin.
+TB_DEV void wf2_push_trace(Wf2Shared& S, const DScene& sc, bool split, int q, bool flag, int s)
+{
+    if (!split) {
+        wf2_push(S, q, flag, s);
+        return;
+    }
+    bool big = false;
+    if (flag) {
+        V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
+        V3 d = v3(S.dx[s], S.dy[s], S.dz[s]);
+        if (((S.flags[s] >> 3) & 1u) != WF2_PH_EXT) {
+            o = o + d * S.ht[s];
+            d = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
+        }
+        V3 rcp;
+        rcp.x = 1.0f / d.x;
+        rcp.y = 1.0f / d.y;
+        rcp.z = 1.0f / d.z;
+        float t;
+        big = ray_aabb(o, rcp, sc.splitLo.x, sc.splitLo.y, sc.splitLo.z, sc.splitHi.x, sc.splitHi.y, sc.splitHi.z, t);
+    }
+    wf2_push(S, q, flag && !big, s);
+    wf2_push(S, WF2_Q_TM, flag && big, s);
 }
 
 // Claim up to 32 entries of queue q for this warp.  Returns the number claimed (warp-uniform);
@@ -282,7 +313,16 @@ TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf
 // THREADS: 512 (16 warps, up to 128 registers) for scenes held in shared memory, where more warps
 // only add instruction-cache pressure; 768 (24 warps, 80 registers) for scenes with deep mesh BVHs,
 // whose traversal is latency bound on L2 and pays for the extra warps (LaunchParams::wideCta).
-template <int THREADS>
+// MODE selects the scheduler that is compiled in -- measured, not principled: the kernel's speed is
+// sensitive to register allocation and code layout, so every variant that is not needed is kept out
+// of the others' bodies (profiles/README.md, steps 12-14):
+//   WF2_MODE_GENERIC  both schedulers, run-time flag, no split trace queue (the free-running default;
+//                     its own specialisation measured 5 % slower on cornell)
+//   WF2_MODE_HARD     hard phases only (veach +4 %)
+//   WF2_MODE_SPLIT    free-running with the split trace queue TM (scenes with a big mesh)
+enum { WF2_MODE_GENERIC = 0, WF2_MODE_HARD = 1, WF2_MODE_SPLIT = 2 };
+
+template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(LaunchParams P, unsigned long long total)
 {
     extern __shared__ __align__(16) unsigned char wf_smem_raw[];
@@ -321,10 +361,11 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
         S.ring[WF2_Q_B][s] = 0;
         S.ring[WF2_Q_F0][s] = 0;
         S.ring[WF2_Q_F1][s] = 0;
+        S.ring[WF2_Q_TM][s] = 0;
         S.sample[s] = 0xffffffffu;
     }
     if (tid == 0) {
-        for (int q = 0; q < 6; ++q) S.head[q] = S.tail[q] = 0u;
+        for (int q = 0; q < 7; ++q) S.head[q] = S.tail[q] = 0u;
         S.tail[WF2_Q_R] = TB_WF2_PATHS;
         S.snap[0] = TB_WF2_PATHS;
         S.snap[1] = S.snap[2] = S.snap[3] = S.snap[4] = 0u;
@@ -348,7 +389,8 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     //    CTA-wide preferred stage and moving on cyclically when that queue has no full chunk left
     //    (dragging the preference along).  Nobody ever waits for a slow ray, which wins when ray
     //    cost varies wildly (deep mesh BVHs) and the hot loop is small enough to stay cached.
-    const bool hard = P.hardPhases != 0;
+    const bool hard = MODE == WF2_MODE_HARD ? true : MODE == WF2_MODE_SPLIT ? false : (P.hardPhases != 0);
+    constexpr bool split = MODE == WF2_MODE_SPLIT;
     // hard-phase schedule: each cycle is two block-synchronous phases,
     //   phase 0:  R (finished slots -> fresh camera rays into F[cycle&1]),  T,  F[~cycle&1]
     //   phase 1:  A,  B
@@ -404,13 +446,26 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             int p = 0;
             if (lane == 0) p = *(volatile int*)&S.pref;
             p = __shfl_sync(0xffffffffu, p, 0);
-            for (int k = 0; k < 8 && stage < 0; ++k) {
-                // k = 0..3: full chunks only; k = 4..7: whatever is left
-                const int q = (p + k) & 3;
-                n = wf2_claim(S, q, k < 4 ? 32 : 1, s);
-                if (n > 0) stage = q;
+            if (!split) {
+                for (int k = 0; k < 8 && stage < 0; ++k) {
+                    // k = 0..3: full chunks only; k = 4..7: whatever is left
+                    const int q = (p + k) & 3;
+                    n = wf2_claim(S, q, k < 4 ? 32 : 1, s);
+                    if (n > 0) stage = q;
+                }
+            } else {
+                // same sweep over five queues: T, TM, A, B, R (pref holds the position in this order)
+                for (int k = 0; k < 10 && stage < 0; ++k) {
+                    const int pos = (p + k) % 5;
+                    const int q = pos == 0 ? WF2_Q_T : pos == 1 ? WF2_Q_TM : pos == 2 ? WF2_Q_A : pos == 3 ? WF2_Q_B : WF2_Q_R;
+                    n = wf2_claim(S, q, k < 5 ? 32 : 1, s);
+                    if (n > 0) {
+                        stage = q;
+                        if (pos != p && lane == 0) *(volatile int*)&S.pref = pos;
+                    }
+                }
             }
-            if (stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
+            if (!split && stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
             if (stage < 0) {
                 if (*(volatile int*)&S.live <= 0) break;
                 __nanosleep(200);
@@ -481,7 +536,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                 }
             }
             __threadfence_block();
-            wf2_push(S, hard ? WF2_Q_F0 + (cycle & 1) : WF2_Q_T, fresh, s);
+            wf2_push_trace(S, sc, split, hard ? WF2_Q_F0 + (cycle & 1) : WF2_Q_T, fresh, s);
             // slots that could not be refilled die: the CTA exits when none is left
             const unsigned dead = __ballot_sync(0xffffffffu, active && !fresh);
             if (dead && lane == 0) atomicSub(&S.live, __popc(dead));
@@ -578,7 +633,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                 }
             }
             __threadfence_block();
-            wf2_push(S, WF2_Q_T, cont, s);
+            wf2_push_trace(S, sc, split, WF2_Q_T, cont, s);
             wf2_push(S, WF2_Q_R, fin, s);
         } else {
             // ===================== B: shadow-ray results ==========================================
@@ -623,20 +678,20 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                 }
             }
             __threadfence_block();
-            wf2_push(S, WF2_Q_T, cont, s);
+            wf2_push_trace(S, sc, split, WF2_Q_T, cont, s);
             wf2_push(S, WF2_Q_R, fin, s);
         }
     }
 }
 
-template <int THREADS>
+template <int THREADS, int MODE>
 static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long total)
 {
     static bool configured = false;
     static int ctasPerSM = 0;
     if (!configured) {
-        cudaFuncSetAttribute(k_wavefront2<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wf2Shared));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_wavefront2<THREADS>, THREADS, sizeof(Wf2Shared)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_wavefront2<THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wf2Shared));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_wavefront2<THREADS, MODE>, THREADS, sizeof(Wf2Shared)) != cudaSuccess ||
             ctasPerSM < 1)
             ctasPerSM = 1;
         configured = true;
@@ -646,7 +701,7 @@ static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t 
     int grid = (numSMs > 0 ? numSMs : 148) * ctasPerSM;
     if (want < (unsigned long long)grid) grid = (int)want;
     if (grid < 1) grid = 1;
-    k_wavefront2<THREADS><<<grid, THREADS, sizeof(Wf2Shared), stream>>>(p, total);
+    k_wavefront2<THREADS, MODE><<<grid, THREADS, sizeof(Wf2Shared), stream>>>(p, total);
 }
 
 void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
@@ -654,9 +709,14 @@ void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, u
     const unsigned long long total = p.samplesPerFrame * (unsigned long long)p.numFrames;
     if (total == 0ull) return;
     cudaMemsetAsync(p.sampleCounter, 0, sizeof(unsigned long long), stream);
-    if (p.wideCta)
-        launch_wavefront2_t<TB_WF2_THREADS_WIDE>(p, numSMs, stream, total);
-    else
-        launch_wavefront2_t<TB_WF2_THREADS>(p, numSMs, stream, total);
+    const bool split = !p.hardPhases && p.scene.splitValid;
+    if (p.wideCta) {
+        if (split) launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_SPLIT>(p, numSMs, stream, total);
+        else launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_GENERIC>(p, numSMs, stream, total);
+    } else {
+        if (p.hardPhases) launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_HARD>(p, numSMs, stream, total);
+        else if (split) launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_SPLIT>(p, numSMs, stream, total);
+        else launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_GENERIC>(p, numSMs, stream, total);
+    }
     if (launchCount) ++*launchCount;
 }
