@@ -72,3 +72,53 @@ def test_product_does_not_reference_oracle():
                     if re.search(r'(#include\s+"[^"]*oracle|import\s+refdrv|from\s+oracle|libtinsel_oracle|libtinsel_ref)', s):
                         bad.append((f, s))
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_error_behaviour_through_the_c_abi(lib):
+    """The reference interface has no error channel (void returns, no exceptions): failures come
+    back as -1 with a sticky message in tb200_last_error(), the caller's buffer is left untouched
+    and the renderer stays usable."""
+    snap = tb.Snapshot(tb.scene_path("cornell"))
+    cam, opt = snap.camera, snap.options
+    opt.width, opt.height = 32, 24
+    r = tb.Renderer(snap.scene)
+    out = np.full((24, 32, 4), 7.0, np.float32)
+    fp = out.ctypes.data_as(C.POINTER(C.c_float))
+    # Render before Init
+    assert lib.tb200_render(r.h, C.byref(cam), C.byref(opt), fp) == -1
+    assert "tb200_init" in tb.last_error() and (out == 7.0).all()
+    assert lib.tb200_finish(r.h, 1.0, 1.5, fp, None) == -1
+    r.Init(32, 24)
+    # options that disagree with the last Init
+    opt.width = 40
+    assert lib.tb200_render(r.h, C.byref(cam), C.byref(opt), fp) == -1
+    assert "differ" in tb.last_error() and (out == 7.0).all()
+    opt.width = 32
+    # null arguments, bad sizes, bad shards, bad row ranges
+    assert lib.tb200_render(r.h, None, C.byref(opt), fp) == -1
+    assert lib.tb200_render(r.h, C.byref(cam), C.byref(opt), None) == -1
+    assert lib.tb200_init(r.h, 0, 10) == -1
+    assert lib.tb200_set_shard(r.h, 2, 2) == -1
+    assert lib.tb200_render_device(r.h, C.byref(cam), C.byref(opt), 1, 20, 10) == -1
+    assert lib.tb200_render_n(r.h, C.byref(cam), C.byref(opt), 0, fp) == -1
+    assert lib.tb200_nlm(r.h, 200.0, 1, fp) == -1            # nothing finished yet
+    assert (out == 7.0).all()
+    # eComplexity is a no-op (render.cpp:516-519); the renderer still works afterwards
+    opt.mode = abi.MODE_COMPLEXITY
+    assert lib.tb200_render(r.h, C.byref(cam), C.byref(opt), fp) == 0 and (out == 7.0).all()
+    opt.mode = abi.MODE_PATHTRACE
+    r.Render(cam, opt, out)
+    assert np.isfinite(out).all() and abs(float(out[2:-2, 2:-2, 3].mean()) / float(out[12, 16, 3]) - 1.0) < 0.5
+    assert r.stats().frames == 1 and r.stats().samples == 32 * 24
+    # a bad device ordinal fails in the factory
+    bad = lib.tb200_create(snap.scene, 99)
+    assert not bad and "device" in tb.last_error()
+    # re-Init with another size resets the accumulation
+    r.Init(16, 16)
+    opt.width = opt.height = 16
+    small = np.zeros((16, 16, 4), np.float32)
+    r.Render(cam, opt, small)
+    assert r.stats().frames == 1
+    r.close()
+    snap.close()

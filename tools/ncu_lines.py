@@ -67,9 +67,23 @@ def function_of_line():
     return funcs
 
 
+def mangled_fragment(rep, kernel):
+    """`k_wavefront2<512, 2>` in the report -> `k_wavefront2ILi512ELi2E`, so that the line table of
+    exactly that template instantiation is used (the library holds several)."""
+    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
+    rows = list(csv.reader(io.StringIO(raw)))
+    name = rows[2][rows[0].index("Kernel Name")]
+    m = re.search(r"(\w+)<([^>]*)>", name)
+    if not m or kernel not in m.group(1):
+        return kernel
+    args = "".join("Li%sE" % a.strip() for a in m.group(2).split(","))
+    return "%sI%sE" % (m.group(1), args)
+
+
 def main():
     rep = sys.argv[1]
     kernel = sys.argv[2] if len(sys.argv) > 2 else "k_wavefront"
+    kernel = mangled_fragment(rep, kernel)
     raw = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv"], text=True, stderr=subprocess.DEVNULL)
     rows = list(csv.reader(io.StringIO(raw)))
     # first row: kernel name, second: header
