@@ -15,7 +15,7 @@ from tinsel_b200 import abi
 import refdrv
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SCENES = ["cornell", "veach", "glass", "meshlight", "motionblur", "gloss", "emitter", "furnace", "conservation", "ajax", "env", "many", "mini", "envmini"]
+SCENES = ["cornell", "veach", "glass", "meshlight", "motionblur", "gloss", "emitter", "furnace", "conservation", "ajax", "env", "many", "mini", "envmini", "table", "simple"]
 f32p = C.POINTER(C.c_float)
 
 

@@ -27,6 +27,8 @@ SCENES = {
     "env": (160, 160),
     "many": (120, 80),     # 22 primitives: reference-order BVH walk instead of the flat scene program
     "mini": (96, 64),      # glass sphere (specular transmission, Beer-Lambert medium) under a gradient sky
+    "table": (160, 100),   # 15 primitives, 5 meshes (prisms, cubes, quads) on a table: glass, metal, many instances
+    "simple": (96, 48),    # two primitives
     "envmini": (128, 96),  # HDR-probe lighting only (synthetic 128x64 probe): ProbeSample / ProbePdf / ProbeEval
 }
 

@@ -9,9 +9,8 @@
 // HBM only sees scene misses and the framebuffer reductions.
 //
 // Every slot that is alive has exactly one pending ray: its extension ray or one shadow ray, and
-// sits in exactly one of four CTA-shared stage queues.  There are NO block-wide barriers in the
-// main loop: each WARP independently claims a chunk of up to 32 entries from a stage queue,
-// processes it and appends the slots to the queues of their next stages:
+// sits in exactly one CTA-shared stage queue.  Each WARP claims a chunk of up to 32 entries from a
+// stage queue, processes it and appends the slots to the queues of their next stages:
 //
 //   R  finish + regenerate: splat the finished sample into the accumulator, claim a new sample
 //      index from the global counter (one atomic per warp), generate its camera ray      -> T
@@ -21,13 +20,17 @@
 //      update and next extension ray -> T, or termination -> R
 //
 // The queues are lock-free rings in shared memory: producers reserve cells with one warp-
-// aggregated atomicAdd on `tail` (ballot + prefix sum) and store lap-tagged slot ids; a consumer
-// warp reads the cells optimistically and takes ownership with one compare-and-swap on `head`,
-// so a chunk is always full while the queue holds >= 32 entries (compaction is implicit in the
-// queue).  Regeneration keeps the slots populated until the sample counter runs dry; the CTA
-// exits when its last slot dies.  Warps never wait for each other, so the divergent cost of
-// individual rays or shading branches no longer stalls the rest of the SM; a shared stage
-// preference keeps them loosely in step so that they share the instruction cache.
+// aggregated atomicAdd on `tail` (ballot + prefix sum) and store lap-tagged slot ids, so a chunk
+// is always full while the queue holds >= 32 entries (compaction is implicit in the queue).
+// Regeneration keeps the slots populated until the sample counter runs dry; the CTA exits when
+// its last slot dies.
+//
+// Who runs what when is the scheduler's business, and there are three of them (template MODE,
+// chosen per scene on the host, see the comment at the kernel): free-running warps with no block
+// barrier at all and a shared stage preference that keeps them loosely in step (they share the
+// instruction cache: 32 KB of L1.5 against ~150 KB of kernel); block-synchronous hard phases with
+// ticket claims for scenes where every hit spawns several shadow rays; and free-running with a
+// second trace queue for rays that enter a big mesh.
 #pragma once
 
 #ifndef TB_WF2_THREADS

@@ -38,6 +38,8 @@ FRAMES = {
     "many": (48, 32, (0, 2)),
     "mini": (48, 32, (0, 2)),
     "envmini": (64, 48, (0, 3)),
+    "table": (64, 40, (0, 2)),
+    "simple": (48, 24, (0,)),
 }
 
 f32p = C.POINTER(C.c_float)

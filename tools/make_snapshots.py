@@ -30,6 +30,8 @@ SCENES = {
     "motionblur": ("motionblur.tin", 0, 0),
     "gloss": ("gloss.tin", 0, 0),
     "emitter": ("emitter.tin", 0, 0),
+    "table": ("table.tin", 0, 0),
+    "simple": ("simple.tin", 0, 0),
     # this repository's own .tin scenes (tests/data): >16 primitives / a glass sphere under a gradient sky
     "many": ("@tests/data/many.tin", 0, 0),
     "mini": ("@tests/data/mini0.tin", 0, 0),
