@@ -222,7 +222,9 @@ def test_both_scheduling_modes_bit_exact(sched, cta):
     os.environ["TINSEL_B200_SPLIT"] = "1" if sched == "split" else "0"
     os.environ["TINSEL_B200_CTA"] = cta
     try:
-        for name in ("veach", "meshlight", "many", "envmini", "glass"):
+        for name in ("veach", "meshlight", "many", "envmini", "glass", "table", "ajax"):
+            if not _available(name):
+                continue
             snap, cam, opt, ref, r = _setup(name, "wavefront")
             rad, _ = r.trace_frame(cam, opt, 3)
             rrad, _ = ref.trace_frame(3, nthreads=8)
