@@ -264,6 +264,21 @@ int tb200_snapshot_save(const char* path, const tb200_scene* scene, const tb200_
                         const tb200_options* options);
 void tb200_snapshot_free(tb200_snapshot* s);
 
+/* ---- tinsel binary meshes (".bin") --------------------------------------------------------------
+ * The reference's own mesh cache (src/mesh.cpp:809-880, ImportMeshFromBin / ExportMeshToBin, written
+ * by `tinsel -convert`, src/main.cpp:151-169): int numVertices, numIndices, numNodes; Vec3
+ * positions[numVertices]; Vec3 normals[numVertices]; int indices[numIndices]; BVHNode
+ * nodes[numNodes]; float area; float cdf[numIndices/3].  It holds exactly what a tb200_mesh needs --
+ * geometry, the built SAH BVH and the light-sampling CDF -- so a host can assemble a tb200_scene from
+ * cached meshes without the OBJ/PLY importers and the BVH builder (3.5 s for ajax).
+ * The loaded object owns the arrays the returned tb200_mesh points into; files written by
+ * tb200_mesh_bin_save are byte-identical to the reference writer's. */
+typedef struct tb200_mesh_file tb200_mesh_file;
+tb200_mesh_file* tb200_mesh_bin_load(const char* path);            /* NULL on failure (tb200_last_error) */
+const tb200_mesh* tb200_mesh_bin_mesh(const tb200_mesh_file* f);
+int tb200_mesh_bin_save(const char* path, const tb200_mesh* mesh);  /* 0 on success */
+void tb200_mesh_bin_free(tb200_mesh_file* f);
+
 #ifdef __cplusplus
 }
 #endif

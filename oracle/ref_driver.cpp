@@ -410,6 +410,44 @@ void ref_nlm(const float* in, float* out, int width, int height, float falloff, 
     NonLocalMeansFilter((const Color*)in, (Color*)out, width, height, falloff, radius);
 }
 
+// The reference's own binary mesh writer / reader (src/mesh.cpp:809-880) for the mesh cache tests.
+int ref_mesh_bin_export(void* h, int meshIndex, const char* path)
+{
+    RefScene* rs = (RefScene*)h;
+    if (meshIndex < 0 || meshIndex >= (int)rs->xmeshes.size()) return -1;
+    const tb200_mesh& g = rs->xmeshes[meshIndex];
+    Mesh m;   // ~Mesh deletes bvh.nodes: give it copies
+    m.positions.assign((const Vec3*)g.positions, (const Vec3*)g.positions + g.numVertices);
+    m.normals.assign((const Vec3*)g.normals, (const Vec3*)g.normals + g.numVertices);
+    m.indices.assign(g.indices, g.indices + g.numIndices);
+    m.cdf.assign(g.cdf, g.cdf + g.numIndices / 3);
+    m.area = g.area;
+    m.bvh.nodes = new BVHNode[g.numNodes];
+    memcpy(m.bvh.nodes, g.nodes, sizeof(BVHNode) * g.numNodes);
+    m.bvh.numNodes = g.numNodes;
+    ExportMeshToBin(path, &m);
+    return 0;
+}
+void* ref_mesh_bin_import(const char* path) { return ImportMeshFromBin(path); }
+void ref_mesh_bin_info(void* mesh, int* counts, float* area)
+{
+    const Mesh* m = (const Mesh*)mesh;
+    counts[0] = (int)m->positions.size();
+    counts[1] = (int)m->indices.size();
+    counts[2] = m->bvh.numNodes;
+    *area = m->area;
+}
+void ref_mesh_bin_copy(void* mesh, float* positions, float* normals, int* indices, void* nodes, float* cdf)
+{
+    const Mesh* m = (const Mesh*)mesh;
+    memcpy(positions, m->positions.data(), m->positions.size() * sizeof(Vec3));
+    memcpy(normals, m->normals.data(), m->normals.size() * sizeof(Vec3));
+    memcpy(indices, m->indices.data(), m->indices.size() * sizeof(int));
+    memcpy(nodes, m->bvh.nodes, sizeof(BVHNode) * m->bvh.numNodes);
+    memcpy(cdf, m->cdf.data(), m->cdf.size() * sizeof(float));
+}
+void ref_mesh_bin_free(void* mesh) { delete (Mesh*)mesh; }
+
 // One frame, no filtering: radiance[3p..] = PathTrace result, raster[2p..] = (x,y) of pixel p.
 void ref_trace_frame(void* h, int frame, float* radiance, float* raster, int nthreads)
 {

@@ -80,6 +80,13 @@ def load_ref(flavour="detmath"):
     lib.ref_finish.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
     lib.ref_write_png.argtypes = [_f32p, C.c_int, C.c_int, C.c_char_p]
     lib.ref_nlm.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_int]
+    lib.ref_mesh_bin_export.restype = C.c_int
+    lib.ref_mesh_bin_export.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    lib.ref_mesh_bin_import.restype = C.c_void_p
+    lib.ref_mesh_bin_import.argtypes = [C.c_char_p]
+    lib.ref_mesh_bin_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    lib.ref_mesh_bin_copy.argtypes = [C.c_void_p, _f32p, _f32p, C.POINTER(C.c_int), C.c_void_p, _f32p]
+    lib.ref_mesh_bin_free.argtypes = [C.c_void_p]
     _libs[flavour] = lib
     return lib
 

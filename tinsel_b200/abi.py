@@ -173,10 +173,22 @@ EXPORTS = [
     "tb200_snapshot_options",
     "tb200_snapshot_save",
     "tb200_snapshot_free",
+    "tb200_mesh_bin_load",
+    "tb200_mesh_bin_mesh",
+    "tb200_mesh_bin_save",
+    "tb200_mesh_bin_free",
 ]
 
 
 def declare_snapshot_api(lib):
+    lib.tb200_mesh_bin_load.restype = C.c_void_p
+    lib.tb200_mesh_bin_load.argtypes = [C.c_char_p]
+    lib.tb200_mesh_bin_mesh.restype = C.POINTER(Mesh)
+    lib.tb200_mesh_bin_mesh.argtypes = [C.c_void_p]
+    lib.tb200_mesh_bin_save.restype = C.c_int
+    lib.tb200_mesh_bin_save.argtypes = [C.c_char_p, C.POINTER(Mesh)]
+    lib.tb200_mesh_bin_free.restype = None
+    lib.tb200_mesh_bin_free.argtypes = [C.c_void_p]
     lib.tb200_snapshot_load.restype = C.c_void_p
     lib.tb200_snapshot_load.argtypes = [C.c_char_p]
     lib.tb200_snapshot_scene.restype = C.POINTER(Scene)

@@ -250,3 +250,88 @@ extern "C" uint32_t tb200_sample_seed(uint32_t pixelIndex, uint32_t frame)
     uint32_t h = tb_mix32(pixelIndex + 0x9E3779B9u);
     return tb_mix32(h ^ (frame * 0x85EBCA6Bu + 0xC2B2AE35u));
 }
+
+
+// ---- tinsel binary meshes (src/mesh.cpp:809-880) ----------------------------------------------------
+struct tb200_mesh_file {
+    std::vector<float> positions, normals, cdf;
+    std::vector<int32_t> indices;
+    std::vector<tb200_bvh_node> nodes;
+    tb200_mesh mesh;
+};
+
+extern "C" tb200_mesh_file* tb200_mesh_bin_load(const char* path)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        g_snapError = std::string("cannot open ") + path;
+        return nullptr;
+    }
+    int32_t counts[3] = {0, 0, 0};   // numVertices, numIndices, numNodes
+    bool ok = fread(counts, 4, 3, f) == 3;
+    // the format has no magic: reject counts the file cannot hold
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    fseek(f, 12, SEEK_SET);
+    ok = ok && counts[0] >= 0 && counts[1] >= 0 && counts[2] >= 0 && counts[1] % 3 == 0;
+    const long long expect = 12ll + 24ll * counts[0] + 4ll * counts[1] + 32ll * counts[2] + 4ll + 4ll * (counts[1] / 3);
+    ok = ok && expect == (long long)size;
+    if (!ok) {
+        fclose(f);
+        g_snapError = std::string("not a tinsel .bin mesh (size does not match its header): ") + path;
+        return nullptr;
+    }
+    tb200_mesh_file* m = new tb200_mesh_file();
+    m->positions.resize(size_t(counts[0]) * 3);
+    m->normals.resize(size_t(counts[0]) * 3);
+    m->indices.resize(size_t(counts[1]));
+    m->nodes.resize(size_t(counts[2]));
+    m->cdf.resize(size_t(counts[1]) / 3);
+    float area = 0.0f;
+    auto rd = [&](void* dst, size_t bytes) { return bytes == 0 || fread(dst, 1, bytes, f) == bytes; };
+    ok = rd(m->positions.data(), m->positions.size() * 4) && rd(m->normals.data(), m->normals.size() * 4) &&
+         rd(m->indices.data(), m->indices.size() * 4) && rd(m->nodes.data(), m->nodes.size() * sizeof(tb200_bvh_node)) &&
+         rd(&area, 4) && rd(m->cdf.data(), m->cdf.size() * 4);
+    fclose(f);
+    if (!ok) {
+        delete m;
+        g_snapError = std::string("short read: ") + path;
+        return nullptr;
+    }
+    m->mesh.positions = m->positions.data();
+    m->mesh.normals = m->normals.data();
+    m->mesh.indices = m->indices.data();
+    m->mesh.nodes = m->nodes.data();
+    m->mesh.cdf = m->cdf.data();
+    m->mesh.numVertices = counts[0];
+    m->mesh.numIndices = counts[1];
+    m->mesh.numNodes = counts[2];
+    m->mesh.area = area;
+    return m;
+}
+
+extern "C" const tb200_mesh* tb200_mesh_bin_mesh(const tb200_mesh_file* f) { return f ? &f->mesh : nullptr; }
+
+extern "C" int tb200_mesh_bin_save(const char* path, const tb200_mesh* g)
+{
+    if (!path || !g) {
+        g_snapError = "tb200_mesh_bin_save: null argument";
+        return -1;
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        g_snapError = std::string("cannot open for writing ") + path;
+        return -1;
+    }
+    const int32_t counts[3] = {g->numVertices, g->numIndices, g->numNodes};
+    bool ok = fwrite(counts, 4, 3, f) == 3;
+    auto wr = [&](const void* src, size_t bytes) { return bytes == 0 || fwrite(src, 1, bytes, f) == bytes; };
+    ok = ok && wr(g->positions, size_t(g->numVertices) * 12) && wr(g->normals, size_t(g->numVertices) * 12) &&
+         wr(g->indices, size_t(g->numIndices) * 4) && wr(g->nodes, size_t(g->numNodes) * sizeof(tb200_bvh_node)) &&
+         wr(&g->area, 4) && wr(g->cdf, size_t(g->numIndices) / 3 * 4);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) g_snapError = std::string("write failed: ") + path;
+    return ok ? 0 : -1;
+}
+
+extern "C" void tb200_mesh_bin_free(tb200_mesh_file* f) { delete f; }
