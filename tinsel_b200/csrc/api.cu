@@ -15,14 +15,18 @@
 #include "tb_kernels.cuh"
 
 const char* tb200_snapshot_error();   // snapshot.cpp
+unsigned long long tb200_snapshot_error_stamp();
+unsigned long long tb200_error_tick();
 
 namespace {
 
 thread_local std::string g_error;
+thread_local unsigned long long g_errorStamp = 0;
 
 bool set_error(const std::string& what)
 {
     g_error = what;
+    g_errorStamp = tb200_error_tick();
     fprintf(stderr, "[tinsel_b200] %s\n", what.c_str());
     return false;
 }
@@ -692,8 +696,11 @@ extern "C" {
 
 const char* tb200_last_error(void)
 {
-    if (!g_error.empty()) return g_error.c_str();
-    return tb200_snapshot_error();
+    // two sticky messages (this file's and snapshot.cpp's): the more recent one
+    if (!g_error.empty() && g_errorStamp > tb200_snapshot_error_stamp()) return g_error.c_str();
+    const char* snap = tb200_snapshot_error();
+    if (snap && snap[0]) return snap;
+    return g_error.c_str();
 }
 
 tb200_renderer* tb200_create(const tb200_scene* scene, int device)

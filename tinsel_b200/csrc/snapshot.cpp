@@ -22,7 +22,16 @@ namespace {
 
 const char kMagic[8] = {'T', 'B', '2', 'S', 'N', 'A', 'P', '1'};
 
+// g_snapError is assigned through snap_error() so that tb200_last_error() can tell which of the two
+// sticky messages (this file's, api.cu's) is the more recent one
 thread_local std::string g_snapError;
+thread_local unsigned long long g_snapStamp = 0;
+thread_local unsigned long long g_errorClock = 0;
+static void snap_error(const std::string& what)
+{
+    g_snapError = what;
+    g_snapStamp = ++g_errorClock;
+}
 
 struct MeshStore {
     std::vector<float> positions, normals, cdf;
@@ -88,7 +97,7 @@ extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
 {
     FILE* f = fopen(path, "rb");
     if (!f) {
-        g_snapError = std::string("cannot open snapshot ") + path;
+        snap_error(std::string("cannot open snapshot ") + path);
         return nullptr;
     }
     tb200_snapshot* s = new tb200_snapshot();
@@ -162,7 +171,7 @@ extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
     }
     fclose(f);
     if (!ok) {
-        g_snapError = std::string("truncated or malformed snapshot ") + path;
+        snap_error(std::string("truncated or malformed snapshot ") + path);
         delete s;
         return nullptr;
     }
@@ -182,7 +191,7 @@ extern "C" int tb200_snapshot_save(const char* path, const tb200_scene* scene, c
 {
     FILE* f = fopen(path, "wb");
     if (!f) {
-        g_snapError = std::string("cannot open for writing ") + path;
+        snap_error(std::string("cannot open for writing ") + path);
         return -1;
     }
     uint32_t hdr[6] = {uint32_t(scene->numPrimitives), uint32_t(scene->numMeshes), uint32_t(scene->numBvhNodes),
@@ -220,7 +229,7 @@ extern "C" int tb200_snapshot_save(const char* path, const tb200_scene* scene, c
     }
     bool ok = ferror(f) == 0;
     fclose(f);
-    if (!ok) g_snapError = std::string("write failed for ") + path;
+    if (!ok) snap_error(std::string("write failed for ") + path);
     return ok ? 0 : -1;
 }
 
@@ -231,6 +240,8 @@ extern "C" void tb200_snapshot_free(tb200_snapshot* s) { delete s; }
 
 // shared with api.cu through tb200_last_error()
 const char* tb200_snapshot_error() { return g_snapError.c_str(); }
+unsigned long long tb200_snapshot_error_stamp() { return g_snapStamp; }
+unsigned long long tb200_error_tick() { return ++g_errorClock; }
 
 // Per-(pixel, frame) seed for Random(seed) (src/maths.h:1040-1044).  Two rounds of a 32-bit
 // bijective mixer: within a frame distinct pixels can never share a seed.  The device copy is
@@ -264,7 +275,7 @@ extern "C" tb200_mesh_file* tb200_mesh_bin_load(const char* path)
 {
     FILE* f = fopen(path, "rb");
     if (!f) {
-        g_snapError = std::string("cannot open ") + path;
+        snap_error(std::string("cannot open ") + path);
         return nullptr;
     }
     int32_t counts[3] = {0, 0, 0};   // numVertices, numIndices, numNodes
@@ -278,7 +289,7 @@ extern "C" tb200_mesh_file* tb200_mesh_bin_load(const char* path)
     ok = ok && expect == (long long)size;
     if (!ok) {
         fclose(f);
-        g_snapError = std::string("not a tinsel .bin mesh (size does not match its header): ") + path;
+        snap_error(std::string("not a tinsel .bin mesh (size does not match its header): ") + path);
         return nullptr;
     }
     tb200_mesh_file* m = new tb200_mesh_file();
@@ -295,7 +306,7 @@ extern "C" tb200_mesh_file* tb200_mesh_bin_load(const char* path)
     fclose(f);
     if (!ok) {
         delete m;
-        g_snapError = std::string("short read: ") + path;
+        snap_error(std::string("short read: ") + path);
         return nullptr;
     }
     m->mesh.positions = m->positions.data();
@@ -315,12 +326,12 @@ extern "C" const tb200_mesh* tb200_mesh_bin_mesh(const tb200_mesh_file* f) { ret
 extern "C" int tb200_mesh_bin_save(const char* path, const tb200_mesh* g)
 {
     if (!path || !g) {
-        g_snapError = "tb200_mesh_bin_save: null argument";
+        snap_error("tb200_mesh_bin_save: null argument");
         return -1;
     }
     FILE* f = fopen(path, "wb");
     if (!f) {
-        g_snapError = std::string("cannot open for writing ") + path;
+        snap_error(std::string("cannot open for writing ") + path);
         return -1;
     }
     const int32_t counts[3] = {g->numVertices, g->numIndices, g->numNodes};
@@ -330,7 +341,7 @@ extern "C" int tb200_mesh_bin_save(const char* path, const tb200_mesh* g)
          wr(g->indices, size_t(g->numIndices) * 4) && wr(g->nodes, size_t(g->numNodes) * sizeof(tb200_bvh_node)) &&
          wr(&g->area, 4) && wr(g->cdf, size_t(g->numIndices) / 3 * 4);
     ok = (fclose(f) == 0) && ok;
-    if (!ok) g_snapError = std::string("write failed: ") + path;
+    if (!ok) snap_error(std::string("write failed: ") + path);
     return ok ? 0 : -1;
 }
 
