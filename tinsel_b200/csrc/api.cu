@@ -306,6 +306,11 @@ struct tb200_renderer {
     int pipeline = 2;             // 0 = mega (validation), 2 = wavefront (product)
     int hardPhases = 1;           // wavefront scheduling mode (see wavefront2.cuh)
     int wideCta = 0;              // 768-thread CTAs for deep mesh BVHs (see wavefront2.cuh)
+    // Split trace queue on/off is decided by measurement (every variant produces the same bits): the
+    // second and third sizeable launches after tb200_create time one setting each, the faster stays.
+    int tunePhase = 3;            // 0 warm-up (split), 1 measuring split, 2 measuring no split, 3 decided
+    double tuneRate[2] = {0.0, 0.0};   // samples per ms with / without the split queue
+    unsigned long long launchSamples = 0;   // samples of the launch whose time is in stats.gpuMs
     tb200_stats stats;
 };
 
@@ -442,6 +447,7 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
             }
         }
         if (split && atoi(split) == 0) r->scene.splitValid = 0;
+        r->tunePhase = (r->scene.splitValid && !split && !r->hardPhases) ? 0 : 3;   // an explicit TINSEL_B200_SPLIT is final
         const char* cta = getenv("TINSEL_B200_CTA");
         if (cta && atoi(cta) == 768) r->wideCta = 1;
         if (cta && atoi(cta) == 512) r->wideCta = 0;
@@ -535,6 +541,7 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
         return set_error("options.width/height differ from the last tb200_init");
     memset(P, 0, sizeof(*P));
     P->scene = r->scene;
+    if (r->tunePhase == 2) P->scene.splitValid = 0;
     camera_setup(*camera, o->width, o->height, &P->camera);
     P->film.width = o->width;
     P->film.height = o->height;
@@ -590,8 +597,22 @@ bool launch_frames(tb200_renderer* r, LaunchParams& P, bool recordStart = true)
         uint64_t rows = 0;
         for (int t = P.shard; t * 4 < P.numRows; t += P.numShards) rows += (uint64_t)((P.numRows - t * 4) < 4 ? (P.numRows - t * 4) : 4);
         r->stats.samples += rows * (uint64_t)P.film.width * (uint64_t)P.numFrames;
+        r->launchSamples = rows * (uint64_t)P.film.width * (uint64_t)P.numFrames;
     }
     return true;
+}
+
+// called once the time of a path-tracing launch is in stats.gpuMs
+void tune_update(tb200_renderer* r)
+{
+    if (r->tunePhase >= 3 || r->launchSamples < (1ull << 18) || !(r->stats.gpuMs > 0.0)) return;
+    const double rate = (double)r->launchSamples / r->stats.gpuMs;
+    if (r->tunePhase == 1) r->tuneRate[0] = rate;
+    if (r->tunePhase == 2) {
+        r->tuneRate[1] = rate;
+        r->scene.splitValid = r->tuneRate[0] >= r->tuneRate[1] ? 1 : 0;
+    }
+    r->tunePhase += 1;
 }
 
 bool finish_timing(tb200_renderer* r)
@@ -600,6 +621,7 @@ bool finish_timing(tb200_renderer* r)
     float ms = 0.0f;
     TB_CUDA(cudaEventElapsedTime(&ms, r->evStart, r->evStop));
     r->stats.gpuMs = ms;
+    tune_update(r);
     return true;
 }
 
@@ -829,6 +851,7 @@ int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
             float ms = 0.0f;
             cudaEventElapsedTime(&ms, r->evStart, r->evStop);
             r->stats.gpuMs = ms;
+            tune_update(r);
             return 0;
         }
     }
@@ -836,6 +859,7 @@ int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, r->evStart, r->evStop);
     r->stats.gpuMs = ms;
+    if (options->mode == TB200_MODE_PATHTRACE) tune_update(r);
     return 0;
 }
 
