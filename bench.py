@@ -28,9 +28,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENE = "cornell"
+SCENE = "cornell"               # --scene: other BASELINE.json configs (ajax 1024^2, veach 1920x1080, env 2048^2), not the default
 WIDTH = HEIGHT = 1024
 SPP_PER_STEP = 32
+# the other BASELINE.json configurations at their own sizes (--scene): size and spp per step
+OTHER_WORKLOADS = {"ajax": (1024, 1024, 16), "veach": (1920, 1080, 16), "env": (2048, 2048, 16)}
 E2E_CALLS_PER_STEP = 8          # Render() calls (1 spp each) per e2e step
 
 # Algorithmic bytes per camera sample for this workload, counted on the REFERENCE traversal order by
@@ -42,7 +44,11 @@ ALGO_JSON = os.path.join(ROOT, "tools", "algo_bytes.json")
 
 def load_algo_bytes():
     with open(ALGO_JSON) as f:
-        return json.load(f)
+        d = json.load(f)
+    if SCENE != "cornell":
+        o = d["other_scenes"][SCENE]
+        return {"bytes_per_sample": o["bytes_per_sample"], "dram_traffic_bytes_per_launch": None}
+    return d
 
 
 def read_peaks():
@@ -98,8 +104,8 @@ class ClockSampler(threading.Thread):
 
 def workload_config(n_gpus):
     return {
-        "workload": "tinsel data/cornell.tin %dx%d, Gaussian filter, maxDepth 4, %d spp per step" % (WIDTH, HEIGHT, SPP_PER_STEP),
-        "scene": "scenes/cornell.tsnap (snapshot of the reference loader's Scene)",
+        "workload": "tinsel data/%s.tin %dx%d, Gaussian filter, maxDepth from the scene file, %d spp per step" % (SCENE, WIDTH, HEIGHT, SPP_PER_STEP),
+        "scene": "scenes/%s.tsnap (snapshot of the reference loader's Scene)" % SCENE,
         "width": WIDTH, "height": HEIGHT, "spp_per_step": SPP_PER_STEP,
         "sharding": "interleaved 4-row tile rows over %d rank(s); one NCCL sum-reduce of the accumulator at the end" % n_gpus,
         "l2": "flushed between timed steps (256 MiB device write outside the per-step events)",
@@ -333,7 +339,13 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="cornell", choices=["cornell"] + sorted(OTHER_WORKLOADS),
+                    help="BASELINE.json configuration to run (default: configs[1], cornell 1024x1024)")
     args = ap.parse_args()
+    if args.scene != "cornell":
+        global SCENE, WIDTH, HEIGHT, SPP_PER_STEP
+        SCENE = args.scene
+        WIDTH, HEIGHT, SPP_PER_STEP = OTHER_WORKLOADS[args.scene]
     if args.impl == "reference":
         run_reference(args)
     else:

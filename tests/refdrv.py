@@ -21,7 +21,7 @@ def _fp(a):
 
 
 def ref_lib_path(flavour):
-    name = "libtinsel_ref.so" if flavour == "literal" else "libtinsel_ref_detmath.so"
+    name = {"literal": "libtinsel_ref.so", "fast": "libtinsel_ref_fast.so"}.get(flavour, "libtinsel_ref_detmath.so")
     return os.path.join(REF_DIR, name)
 
 

@@ -66,5 +66,6 @@ if __name__ == "__main__":
             old = json.load(open(out))
         res["dram_traffic_bytes_per_launch"] = old.get("dram_traffic_bytes_per_launch")
         res["dram_traffic_source"] = old.get("dram_traffic_source")
+        res["other_scenes"] = old.get("other_scenes")
         json.dump(res, open(out, "w"), indent=1)
         print("wrote", out)
