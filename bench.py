@@ -47,7 +47,8 @@ def load_algo_bytes():
         d = json.load(f)
     if SCENE != "cornell":
         o = d["other_scenes"][SCENE]
-        return {"bytes_per_sample": o["bytes_per_sample"], "dram_traffic_bytes_per_launch": None}
+        return {"bytes_per_sample": o["bytes_per_sample"], "traversal_bytes_per_sample": o.get("traversal_bytes_per_sample"),
+                "dram_traffic_bytes_per_launch": None}
     return d
 
 
@@ -321,6 +322,7 @@ def run_ours(args):
                          "traffic": algo.get("dram_traffic_bytes_per_launch"),
                          "kernel": "k_wavefront2", "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": algo["bytes_per_sample"],
+                         "traversal_bytes_per_sample": algo.get("traversal_bytes_per_sample"),
                          "note": "algorithmic bytes on the reference traversal order; the working set is SMEM/L2 resident so DRAM traffic is far below it"},
             "cpu_baseline": {"value": cpu_msps, "unit": "Msamples/s", "cores": cores, "kind": kind,
                              "sample": "%dx%d image, 2 spp (%.1f s), per-sample-seeded driver over the reference's PathTrace" % (WIDTH, HEIGHT, cpu_dt)},
