@@ -56,6 +56,58 @@ def test_no_cpu_fallback(lib):
     snap.close()
 
 
+def test_create_validates_the_scene_before_touching_the_device(lib):
+    """Indices the kernels would follow are range-checked in tb200_create (runs before the CUDA
+    device is opened, so this works on a CPU-only box too)."""
+    snap = tb.Snapshot(tb.scene_path("glass"))
+    base = snap.scene.contents
+
+    def attempt(mutate):
+        sc = abi.Scene()
+        C.memmove(C.byref(sc), C.byref(base), C.sizeof(abi.Scene))
+        keep = mutate(sc)
+        h = lib.tb200_create(C.byref(sc), 0)
+        if h:
+            lib.tb200_destroy(h)
+        return bool(h), tb.last_error(), keep
+
+    def bad_prim_mesh(sc):
+        prims = (abi.Primitive * sc.numPrimitives)()
+        C.memmove(prims, sc.primitives, C.sizeof(prims))
+        for p in prims:
+            if p.type == 2:
+                p.mesh = sc.numMeshes + 3
+        sc.primitives = C.cast(prims, C.POINTER(abi.Primitive))
+        return prims
+
+    def bad_bvh(sc):
+        nodes = (abi.BvhNode * sc.numBvhNodes)()
+        C.memmove(nodes, sc.bvhNodes, C.sizeof(nodes))
+        nodes[0].left = 10 ** 6
+        nodes[0].right_leaf &= 0x7fffffff
+        sc.bvhNodes = C.cast(nodes, C.POINTER(abi.BvhNode))
+        return nodes
+
+    def bad_index(sc):
+        meshes = (abi.Mesh * sc.numMeshes)()
+        C.memmove(meshes, sc.meshes, C.sizeof(meshes))
+        idx = (C.c_int32 * meshes[0].numIndices)()
+        C.memmove(idx, meshes[0].indices, C.sizeof(idx))
+        idx[5] = meshes[0].numVertices
+        meshes[0].indices = C.cast(idx, C.POINTER(C.c_int32))
+        sc.meshes = C.cast(meshes, C.POINTER(abi.Mesh))
+        return meshes, idx
+
+    def no_prims(sc):
+        sc.numPrimitives = 0
+
+    for mutate, expect in ((bad_prim_mesh, "mesh index out of range"), (bad_bvh, "points outside its array"),
+                           (bad_index, "vertex index out of range"), (no_prims, "no primitives")):
+        ok, err, _ = attempt(mutate)
+        assert not ok and "invalid scene" in err and expect in err, (mutate.__name__, err)
+    snap.close()
+
+
 def test_product_does_not_reference_oracle():
     """The product path must not import / link / include anything under oracle/."""
     bad = []

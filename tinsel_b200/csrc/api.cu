@@ -386,7 +386,8 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
             norms[size_t(t) * 3 + 1] = make_float4(n2[1], n2[2], n3[0], n3[1]);
             norms[size_t(t) * 3 + 2] = make_float4(n3[2], 0.0f, 0.0f, 0.0f);
         }
-        std::vector<float> cdf(g.cdf, g.cdf + numTris);
+        std::vector<float> cdf(size_t(numTris), 0.0f);   // only read when the mesh is sampled as a light
+        if (g.cdf) memcpy(cdf.data(), g.cdf, size_t(numTris) * sizeof(float));
         BvhPair* dPairs;
         float4 *dVerts, *dNorms;
         float* dCdf;
@@ -725,12 +726,71 @@ const char* tb200_last_error(void)
     return g_error.c_str();
 }
 
+// Structural checks on the caller's scene before anything is uploaded: every index the kernels will
+// follow must stay inside its array (the reference trusts its own loader; a C ABI cannot).
+static bool validate_bvh(const tb200_bvh_node* nodes, int numNodes, int numItems, const char* what, std::string* why)
+{
+    if (numNodes <= 0 || !nodes) {
+        *why = std::string(what) + ": no BVH nodes";
+        return false;
+    }
+    for (int i = 0; i < numNodes; ++i) {
+        const bool leaf = (nodes[i].right_leaf >> 31) != 0;
+        const uint32_t left = nodes[i].left, right = nodes[i].right_leaf & 0x7fffffffu;
+        if (leaf ? left >= (uint32_t)numItems : (left >= (uint32_t)numNodes || right >= (uint32_t)numNodes)) {
+            *why = std::string(what) + ": BVH node " + std::to_string(i) + " points outside its array";
+            return false;
+        }
+    }
+    return true;
+}
+
+static bool validate_scene(const tb200_scene* s, std::string* why)
+{
+    if (s->numPrimitives <= 0 || !s->primitives) return *why = "scene has no primitives", false;
+    if (s->numPrimitives > 4095) return *why = "more than 4095 primitives (the wavefront's NEE cursor holds 12-bit primitive indices)", false;
+    if (s->numMeshes < 0 || (s->numMeshes > 0 && !s->meshes)) return *why = "bad mesh array", false;
+    if (!validate_bvh(s->bvhNodes, s->numBvhNodes, s->numPrimitives, "scene", why)) return false;
+    for (int m = 0; m < s->numMeshes; ++m) {
+        const tb200_mesh& g = s->meshes[m];
+        const std::string name = "mesh " + std::to_string(m);
+        if (g.numVertices <= 0 || g.numIndices <= 0 || g.numIndices % 3 != 0 || !g.positions || !g.normals || !g.indices)
+            return *why = name + ": empty or incomplete geometry", false;
+        for (int i = 0; i < g.numIndices; ++i)
+            if (g.indices[i] < 0 || g.indices[i] >= g.numVertices) return *why = name + ": vertex index out of range", false;
+        if (!validate_bvh(g.nodes, g.numNodes, g.numIndices / 3, name.c_str(), why)) return false;
+    }
+    for (int i = 0; i < s->numPrimitives; ++i) {
+        const tb200_primitive& p = s->primitives[i];
+        if (p.type != TB200_SPHERE && p.type != TB200_PLANE && p.type != TB200_MESH)
+            return *why = "primitive " + std::to_string(i) + ": unknown type", false;
+        if (p.type == TB200_MESH && (p.mesh < 0 || p.mesh >= s->numMeshes))
+            return *why = "primitive " + std::to_string(i) + ": mesh index out of range", false;
+        if (p.type == TB200_MESH && p.lightSamples > 0 && !s->meshes[p.mesh].cdf)
+            return *why = "primitive " + std::to_string(i) + ": mesh light without a sampling CDF", false;
+        if (p.lightSamples < 0 || p.lightSamples > 4095) return *why = "primitive " + std::to_string(i) + ": lightSamples out of range", false;
+    }
+    if (s->sky.probeValid) {
+        const tb200_sky& k = s->sky;
+        if (k.probeWidth <= 0 || k.probeHeight <= 0 || !k.probeData || !k.pdfValuesX || !k.cdfValuesX || !k.pdfValuesY || !k.cdfValuesY)
+            return *why = "sky probe: missing tables", false;
+    }
+    return true;
+}
+
 tb200_renderer* tb200_create(const tb200_scene* scene, int device)
 {
     g_error.clear();
     if (!scene) {
         set_error("tb200_create: null scene");
         return nullptr;
+    }
+    {
+        std::string why;
+        if (!validate_scene(scene, &why)) {
+            set_error("tb200_create: invalid scene: " + why);
+            return nullptr;
+        }
     }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
