@@ -668,8 +668,9 @@ bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output, bool rec
     pin_output(r, output);
     const float4* accum = P.accum;
     const size_t rowBytes = size_t(r->width) * sizeof(float4);
-    // bands of whole tile rows, at most TB_MAX_BANDS, about 1 MiB each
-    int bandTileRows = std::max(1, (int)((size_t(1) << 20) / (rowBytes * 4)));
+    // bands of whole tile rows, at most TB_MAX_BANDS, about 256 KiB each: what is left to copy when the
+    // kernel ends is one band plus the filter's reach, and consecutive finished bands go out in one copy
+    int bandTileRows = std::max(1, (int)((size_t(1) << 18) / (rowBytes * 4)));
     bandTileRows = std::max(bandTileRows, (P.tileRows + TB_MAX_BANDS - 1) / TB_MAX_BANDS);
     const int numBands = (P.tileRows + bandTileRows - 1) / bandTileRows;
     // pixel rows a sample of row y splats into: y - reach .. y + reach (render.cpp:404-407)
