@@ -282,7 +282,7 @@ def test_rotated_camera_and_fov():
 
 
 @pytest.mark.parametrize("case", [
-    ("cornell", (1024, 1024), 1, 0.0),    # bench size: 16 bands of 1 MiB
+    ("cornell", (1024, 1024), 1, 0.0),    # bench size: 64 bands of 256 KiB
     ("cornell", (1021, 515), 1, 0.0),     # ragged: tile padding retires through the band counters too
     ("veach", (640, 2048), 1, 0.0),       # hard-phase scheduling, tall image (64 bands)
     ("cornell", (512, 512), 3, 0.0),      # rank 1 of 3: interleaved tile rows
