@@ -253,6 +253,14 @@ class PortScene:
         self.lib.oracle_trace_frame(self.h, C.byref(self.camera), C.byref(o), frame, _fp(rad), _fp(ras), nthreads)
         return rad, ras
 
+    def trace(self, o, d, time=0.0):
+        o = np.asarray(o, np.float32)
+        d = np.asarray(d, np.float32)
+        t = C.c_float()
+        n = np.zeros(3, np.float32)
+        prim = self.lib.oracle_trace(self.h, _fp(o), _fp(d), time, C.byref(t), _fp(n))
+        return prim, t.value, n
+
     def render_normals(self):
         o = self.options
         out = np.zeros((o.height, o.width, 4), np.float32)
