@@ -10,7 +10,8 @@ import tinsel_b200 as tb
 import refdrv
 import fuzzscene
 
-SEEDS = list(range(12))
+SEEDS = list(range(12))            # GPU part (validated on the B200)
+CPU_SEEDS = list(range(48))        # restatement vs the reference's compiled code
 
 
 def _same(a, b):
@@ -18,7 +19,7 @@ def _same(a, b):
 
 
 @pytest.mark.skipif(not refdrv.have_ref("detmath"), reason="oracle/_ref not built")
-@pytest.mark.parametrize("seed", SEEDS)
+@pytest.mark.parametrize("seed", CPU_SEEDS)
 def test_port_matches_reference_on_random_scenes(seed, tmp_path):
     path = str(tmp_path / "fuzz.tsnap")
     what = fuzzscene.make_scene(seed, path)
