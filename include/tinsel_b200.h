@@ -18,6 +18,7 @@
 #ifndef TINSEL_B200_H
 #define TINSEL_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -161,6 +162,19 @@ typedef struct tb200_renderer tb200_renderer;
  * the GPU.  `device` is the CUDA ordinal.  Returns NULL on failure (see tb200_last_error). */
 tb200_renderer* tb200_create(const tb200_scene* scene, int device);
 
+/* The same renderer spread over several GPUs of one box (one process, one host thread per further
+ * device inside the library): the scene is replicated, tb200_init cuts the image into one contiguous
+ * slab of pixel rows per device (cut at 4-row tile rows), every device traces the samples of its slab
+ * plus those of the rows within the filter's reach outside it -- so it holds COMPLETE sums for the
+ * rows it owns, from bit-identical duplicated samples -- and tb200_render has each device
+ * stream its own rows into `output` over its own PCIe link: no per-call reduction, no collective.
+ * Every call below that takes the returned handle acts on the whole group unless it says otherwise.
+ * This is what CreateGpuWavefrontRenderer returns when TINSEL_GPUS=N is set (tinsel_plugin.cpp).
+ * `devices`: numDevices distinct CUDA ordinals; devices[0] is the head (finish / denoise run there). */
+#define TB200_MAX_DEVICES 16
+tb200_renderer* tb200_create_multi(const tb200_scene* scene, const int* devices, int numDevices);
+int tb200_num_devices(const tb200_renderer* r);
+
 /* Replaces Renderer::Init (src/render.h:70; semantics of src/render.cu:1070-1075):
  * (re)allocates and zeroes the device accumulator, resets the frame counter. Returns 0 on success. */
 int tb200_init(tb200_renderer* r, int width, int height);
@@ -184,10 +198,32 @@ int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb2
  * the unsharded image up to fp32 summation order.  Default: shard 0 of 1. */
 int tb200_set_shard(tb200_renderer* r, int shard, int numShards);
 
-/* Launch all work of this renderer on a caller-owned CUDA stream (a cudaStream_t passed as void*),
- * e.g. torch's current stream, so that the caller's own events bracket it.  NULL restores the
- * renderer's private stream. */
-int tb200_set_stream(tb200_renderer* r, void* cudaStream);
+/* external != 0: launch all work of this renderer on the caller's CUDA stream `cudaStream` (a
+ * cudaStream_t passed as void*; handle 0 is CUDA's legacy default stream), so that the caller's own
+ * events bracket it.  external == 0: back to the renderer's private stream (`cudaStream` ignored).
+ * Single-device renderers only. */
+int tb200_set_stream(tb200_renderer* r, void* cudaStream, int external);
+
+/* Owner-computes row slab (the multi-GPU building block, also usable one process per GPU): this
+ * renderer owns pixel rows [firstRow, firstRow+numRows).  It traces their samples plus those of the
+ * rows within the filter's reach outside the slab, splats into the owned rows only, and
+ * tb200_render / tb200_read_accumulator / tb200_render_n write only the owned rows of `output`.
+ * numRows < 0 removes the slab (whole image).  Not combinable with tb200_set_shard. */
+int tb200_set_slab(tb200_renderer* r, int firstRow, int numRows);
+
+/* Page-locks a CALLER-OWNED host buffer (cudaHostRegister, portable across devices) so that the
+ * read-backs of tb200_render & co. into it run at PCIe speed, asynchronously, and -- for a
+ * multi-device renderer -- from all devices at once.  The library never pins caller memory on its
+ * own: the caller owns the buffer's lifetime and must call tb200_unpin_output (or tb200_destroy)
+ * BEFORE freeing or reallocating it.  Unpinned buffers work too, through the driver's staged copy.
+ * Returns 0 on success. */
+int tb200_pin_output(tb200_renderer* r, float* output, size_t bytes);
+int tb200_unpin_output(tb200_renderer* r);
+
+/* Multi-device renderers: copies every device's slab into the head device's accumulator (device to
+ * device, NVLink), so that tb200_device_accumulator(head) holds the whole image.  tb200_finish does
+ * this itself.  No-op for a single device. */
+int tb200_gather_device(tb200_renderer* r);
 
 /* Accumulate into caller-owned DEVICE memory (width*height*4 floats, e.g. a torch tensor that is
  * then reduced with NCCL) instead of the renderer's own buffer.  Call after tb200_init; NULL

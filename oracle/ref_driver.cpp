@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cfloat>
 #include <climits>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -384,6 +385,86 @@ void ref_render_seeded(void* h, int frame0, int nframes, float* out, int nthread
         const int b0 = Max(0, r0 - halo), b1 = Min(H, r1 + halo);
         for (int y = b0; y < b1; ++y)
             for (int x = 0; x < W; ++x) o[y * W + x] += bufs[t][size_t(y - b0) * W + x];
+    }
+}
+
+// The CPU arm of the benchmark (bench.py --impl reference, cpu_baseline): the same seeded loop as
+// ref_render_seeded -- the reference's own PathTrace and AddSample per sample -- with a work
+// distribution that is fair to the CPU: `nthreads` threads pull strips of 4 pixel rows from a shared
+// counter (cost per row is far from uniform: cornell's ceiling rows terminate at once), each strip is
+// accumulated for all `nframes` frames into a private strip buffer with halo rows, and the strips are
+// folded into `out` afterwards in strip order, two passes of non-overlapping strips in parallel.
+// The result does not depend on the thread count.
+void ref_render_pool(void* h, int frame0, int nframes, float* out, int nthreads)
+{
+    RefScene* rs = (RefScene*)h;
+    const Options& options = rs->options;
+    const Camera& camera = rs->camera;
+    const int W = options.width, H = options.height;
+    const int stripRows = 4;
+    const int numStrips = (H + stripRows - 1) / stripRows;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > numStrips) nthreads = numStrips;
+    const int halo = int(options.filter.width) + 1;
+
+    std::vector<std::vector<Color>> strips(numStrips);
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        CpuRenderer cpu(&rs->scene);
+        CameraSampler sampler(Transform(camera.position, camera.rotation), camera.fov, 0.001f, 1.0f, W, H);
+        for (;;) {
+            const int sidx = next.fetch_add(1);
+            if (sidx >= numStrips) break;
+            const int r0 = sidx * stripRows, r1 = Min(H, r0 + stripRows);
+            const int b0 = Max(0, r0 - halo), b1 = Min(H, r1 + halo);
+            std::vector<Color>& buf = strips[sidx];
+            buf.assign(size_t(W) * (b1 - b0), Color());
+            Color* base = buf.data() - size_t(b0) * W;
+            for (int k = frame0; k < frame0 + nframes; ++k)
+                for (int j = r0; j < r1; ++j)
+                    for (int i = 0; i < W; ++i) {
+                        cpu.rand = Random(int(tb200_sample_seed(uint32_t(j * W + i), uint32_t(k))));
+                        float x, y, t;
+                        Sample2D(cpu.rand, x, y);
+                        Sample1D(cpu.rand, t);
+                        float time = Lerp(camera.shutterStart, camera.shutterEnd, t);
+                        x += i;
+                        y += j;
+                        Vec3 origin, dir;
+                        sampler.GenerateRay(x, y, origin, dir);
+                        Vec3 sample = PathTrace(rs->scene, origin, dir, time, options.maxDepth, cpu.rand);
+                        cpu.AddSample(base, W, H, x, y, options.clamp, options.filter, sample);
+                    }
+        }
+    };
+    {
+        std::vector<std::thread> threads;
+        for (int t = 1; t < nthreads; ++t) threads.emplace_back(work);
+        work();
+        for (auto& th : threads) th.join();
+    }
+    // fold: strips whose halos overlap (neighbours, and next-but-one when halo > stripRows/2) must not
+    // run together: `stride` interleaved passes, each over strips `stride` apart
+    Color* o = (Color*)out;
+    const int stride = 1 + (2 * halo + stripRows - 1) / stripRows;
+    for (int pass = 0; pass < stride; ++pass) {
+        std::atomic<int> cursor(pass);
+        auto fold = [&]() {
+            for (;;) {
+                const int sidx = cursor.fetch_add(stride);
+                if (sidx >= numStrips) break;
+                const int r0 = sidx * stripRows, r1 = Min(H, r0 + stripRows);
+                const int b0 = Max(0, r0 - halo), b1 = Min(H, r1 + halo);
+                const std::vector<Color>& buf = strips[sidx];
+                for (int y = b0; y < b1; ++y)
+                    for (int x = 0; x < W; ++x) o[y * W + x] += buf[size_t(y - b0) * W + x];
+            }
+        };
+        std::vector<std::thread> threads;
+        const int nfold = Min(nthreads, 16);
+        for (int t = 1; t < nfold; ++t) threads.emplace_back(fold);
+        fold();
+        for (auto& th : threads) th.join();
     }
 }
 

@@ -36,6 +36,23 @@ def have_reference_tree():
 _libs = {}
 
 
+def ref_gpu_lib_path():
+    return os.path.join(REF_DIR, "libtinsel_ref_gpu.so")
+
+
+def have_ref_gpu():
+    return os.path.exists(ref_gpu_lib_path())
+
+
+def load_ref_gpu():
+    if "gpu" not in _libs:
+        lib = C.CDLL(ref_gpu_lib_path())
+        lib.refgpu_bench.restype = C.c_int
+        lib.refgpu_bench.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, _f32p, C.POINTER(C.c_double)]
+        _libs["gpu"] = lib
+    return _libs["gpu"]
+
+
 def load_ref(flavour="detmath"):
     if flavour in _libs:
         return _libs[flavour]
@@ -60,6 +77,7 @@ def load_ref(flavour="detmath"):
     lib.ref_save_snapshot.argtypes = [C.c_void_p, C.c_char_p]
     lib.ref_render_literal.argtypes = [C.c_void_p, C.c_int, _f32p]
     lib.ref_render_seeded.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int]
+    lib.ref_render_pool.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int]
     lib.ref_trace_frame.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int]
     lib.ref_destroy.argtypes = [C.c_void_p]
     lib.ref_random_u32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint32)]
@@ -151,6 +169,25 @@ class RefScene:
             out = np.zeros((h, w, 4), np.float32)
         self.lib.ref_render_seeded(self.h, frame0, nframes, _fp(out), nthreads)
         return out
+
+    def render_pool(self, frame0, nframes, nthreads=1, out=None):
+        """The benchmark's CPU arm: same samples as render_seeded, dynamic 4-row strips over nthreads."""
+        h, w = self._shape()
+        if out is None:
+            out = np.zeros((h, w, 4), np.float32)
+        self.lib.ref_render_pool(self.h, frame0, nframes, _fp(out), nthreads)
+        return out
+
+    def gpu_bench(self, warmup, calls):
+        """The reference's own GPU renderer (src/render.cu RenderGpu, compiled for sm_100a with its Release
+        flags) on this scene: (wall ms per Render() call, kernel ms per call).  Speed only, not parity."""
+        lib = load_ref_gpu()
+        out = (C.c_double * 2)()
+        rc = lib.refgpu_bench(self.lib.ref_native_scene(self.h), self.lib.ref_native_camera(self.h),
+                              self.lib.ref_native_options(self.h), warmup, calls, None, out)
+        if rc != 0:
+            raise RuntimeError("refgpu_bench failed: %d" % rc)
+        return out[0], out[1]
 
     def trace_frame(self, frame, nthreads=1):
         h, w = self._shape()

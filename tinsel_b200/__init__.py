@@ -49,7 +49,19 @@ def load_library():
     lib.tb200_set_shard.restype = C.c_int
     lib.tb200_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.tb200_set_stream.restype = C.c_int
-    lib.tb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tb200_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.tb200_create_multi.restype = C.c_void_p
+    lib.tb200_create_multi.argtypes = [C.POINTER(Scene), C.POINTER(C.c_int), C.c_int]
+    lib.tb200_num_devices.restype = C.c_int
+    lib.tb200_num_devices.argtypes = [C.c_void_p]
+    lib.tb200_set_slab.restype = C.c_int
+    lib.tb200_set_slab.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.tb200_pin_output.restype = C.c_int
+    lib.tb200_pin_output.argtypes = [C.c_void_p, f32p, C.c_size_t]
+    lib.tb200_unpin_output.restype = C.c_int
+    lib.tb200_unpin_output.argtypes = [C.c_void_p]
+    lib.tb200_gather_device.restype = C.c_int
+    lib.tb200_gather_device.argtypes = [C.c_void_p]
     lib.tb200_bind_accumulator.restype = C.c_int
     lib.tb200_bind_accumulator.argtypes = [C.c_void_p, C.c_void_p]
     lib.tb200_device_accumulator.restype = C.c_void_p
@@ -130,12 +142,18 @@ class Renderer:
                                    receives the running sums (sum w*rgb, sum w)
     """
 
-    def __init__(self, scene, device=0):
+    def __init__(self, scene, device=0, devices=None):
+        """devices: a list of CUDA ordinals -> one renderer spread over several GPUs (tb200_create_multi)."""
         self.lib = load_library()
-        self.h = self.lib.tb200_create(scene, device)
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            self.h = self.lib.tb200_create_multi(scene, arr, len(devices))
+        else:
+            self.h = self.lib.tb200_create(scene, device)
         if not self.h:
             raise TinselB200Error("tb200_create failed: " + last_error())
         self.width = self.height = 0
+        self._pinned = None
 
     def _check(self, rc, what):
         if rc != 0:
@@ -159,7 +177,30 @@ class Renderer:
         self._check(self.lib.tb200_set_shard(self.h, shard, num_shards), "tb200_set_shard")
 
     def set_stream(self, cuda_stream_handle):
-        self._check(self.lib.tb200_set_stream(self.h, C.c_void_p(cuda_stream_handle)), "tb200_set_stream")
+        """None: the renderer's private stream; an int (0 = CUDA's legacy default stream): the caller's."""
+        if cuda_stream_handle is None:
+            self._check(self.lib.tb200_set_stream(self.h, None, 0), "tb200_set_stream")
+        else:
+            self._check(self.lib.tb200_set_stream(self.h, C.c_void_p(cuda_stream_handle), 1), "tb200_set_stream")
+
+    def set_slab(self, first_row, num_rows):
+        self._check(self.lib.tb200_set_slab(self.h, first_row, num_rows), "tb200_set_slab")
+
+    def pin_output(self, array):
+        """Page-locks `array` (which the caller keeps alive until unpin_output / close) for fast read-backs."""
+        assert array.dtype == np.float32 and array.flags["C_CONTIGUOUS"]
+        self._check(self.lib.tb200_pin_output(self.h, _fp(array), array.nbytes), "tb200_pin_output")
+        self._pinned = array   # keeps the buffer alive while it is registered
+
+    def unpin_output(self):
+        self.lib.tb200_unpin_output(self.h)
+        self._pinned = None
+
+    def gather_device(self):
+        self._check(self.lib.tb200_gather_device(self.h), "tb200_gather_device")
+
+    def num_devices(self):
+        return self.lib.tb200_num_devices(self.h)
 
     def bind_accumulator(self, device_ptr):
         self._check(self.lib.tb200_bind_accumulator(self.h, C.c_void_p(device_ptr)), "tb200_bind_accumulator")
@@ -211,8 +252,9 @@ class Renderer:
 
     def close(self):
         if self.h:
-            self.lib.tb200_destroy(self.h)
+            self.lib.tb200_destroy(self.h)   # unpins
             self.h = None
+            self._pinned = None
 
     def __del__(self):
         try:

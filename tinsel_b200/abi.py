@@ -150,6 +150,12 @@ def copy_struct(s):
 # Every symbol include/tinsel_b200.h declares (tests/test_abi.py checks the library exports them all).
 EXPORTS = [
     "tb200_create",
+    "tb200_create_multi",
+    "tb200_num_devices",
+    "tb200_set_slab",
+    "tb200_pin_output",
+    "tb200_unpin_output",
+    "tb200_gather_device",
     "tb200_init",
     "tb200_render",
     "tb200_render_device",

@@ -5,7 +5,12 @@
 // (cited inline) and is compiled without contraction (-Xcompiler -ffp-contract=off, no fast-math)
 // so that it matches the reference's x86-64 build.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -298,10 +303,19 @@ struct tb200_renderer {
     unsigned int bandTag = 0;
     int streamedReadback = 1;             // TINSEL_B200_READBACK=plain turns it off
 
-    // host read-back
-    void* registered = nullptr;   // host pointer currently pinned with cudaHostRegister
+    // host read-back: a caller-owned buffer pinned on request (tb200_pin_output), never implicitly
+    void* registered = nullptr;
     size_t registeredBytes = 0;
-    void* lastOutput = nullptr;
+
+    // owner-computes row slab (tb200_set_slab; slabRows < 0: the whole image)
+    int slabRow0 = 0, slabRows = -1;
+
+    // multi-device group (tb200_create_multi): the head owns one renderer per further device, each
+    // driven by its own host thread
+    std::vector<tb200_renderer*> peers;
+    struct Worker* worker = nullptr;      // peers only
+    std::string workerError;              // a peer's failure message, handed to the calling thread
+    bool peerAccess = false;
 
     int pipeline = 2;             // 0 = mega (validation), 2 = wavefront (product)
     int hardPhases = 1;           // wavefront scheduling mode (see wavefront2.cuh)
@@ -535,6 +549,9 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
     return true;
 }
 
+// pixel rows a sample of row y can splat into: y - reach .. y + reach (render.cpp:404-407)
+int filter_reach(float filterWidth) { return (int)ceilf(std::max(0.0f, filterWidth)) + 1; }
+
 bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_options* o, LaunchParams* P)
 {
     if (!r->dAccum) return set_error("tb200_init has not been called");
@@ -565,6 +582,20 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     P->wideCta = r->wideCta;
     P->firstRow = 0;
     P->numRows = o->height;
+    P->film.rowLo = 0;
+    P->film.rowHi = o->height;
+    if (r->slabRows >= 0) {
+        // owner-computes slab: trace the owned rows plus every row whose samples can reach them
+        // (render.cpp:404-407: a sample of row y splats into rows int(y' - w) .. int(y' + w), y' in [y, y+1]),
+        // splat into the owned rows only
+        const int reach = filter_reach(o->filterWidth);
+        const int lo = std::max(0, std::min(r->slabRow0, o->height));
+        const int hi = std::max(lo, std::min(r->slabRow0 + r->slabRows, o->height));
+        P->film.rowLo = lo;
+        P->film.rowHi = hi;
+        P->firstRow = std::max(0, lo - reach);
+        P->numRows = hi > lo ? std::min(o->height, hi + reach) - P->firstRow : 0;
+    }
     P->shard = r->shard;
     P->numShards = r->numShards;
     finalize_params(P);
@@ -594,9 +625,12 @@ bool launch_frames(tb200_renderer* r, LaunchParams& P, bool recordStart = true)
     TB_CUDA(cudaGetLastError());
     r->stats.kernelLaunches += launches;
     {
-        // samples inside the image (tile padding excluded)
+        // samples inside the image (tile padding excluded; with a slab: the owned rows, not their halo)
         uint64_t rows = 0;
-        for (int t = P.shard; t * 4 < P.numRows; t += P.numShards) rows += (uint64_t)((P.numRows - t * 4) < 4 ? (P.numRows - t * 4) : 4);
+        if (r->slabRows >= 0)
+            rows = (uint64_t)(P.film.rowHi - P.film.rowLo);
+        else
+            for (int t = P.shard; t * 4 < P.numRows; t += P.numShards) rows += (uint64_t)((P.numRows - t * 4) < 4 ? (P.numRows - t * 4) : 4);
         r->stats.samples += rows * (uint64_t)P.film.width * (uint64_t)P.numFrames;
         r->launchSamples = rows * (uint64_t)P.film.width * (uint64_t)P.numFrames;
     }
@@ -626,33 +660,30 @@ bool finish_timing(tb200_renderer* r)
     return true;
 }
 
-// A host buffer that is handed in twice in a row (tinsel's main.cpp passes the same g_pixels every
-// call, src/main.cpp:249) is pinned with cudaHostRegister so the copies run at PCIe speed and
-// asynchronously instead of through the pageable path.
-void pin_output(tb200_renderer* r, float* output)
+// pixel rows [row0, row1) this renderer is responsible for delivering to the host
+void owned_rows(const tb200_renderer* r, int* row0, int* row1)
 {
-    const size_t bytes = size_t(r->width) * r->height * sizeof(float4);
-    if (output == r->lastOutput && r->registered != output) {
-        if (r->registered) {
-            cudaHostUnregister(r->registered);
-            r->registered = nullptr;
-        }
-        if (cudaHostRegister(output, bytes, cudaHostRegisterDefault) == cudaSuccess) {
-            r->registered = output;
-            r->registeredBytes = bytes;
-        } else {
-            cudaGetLastError();   // not fatal: fall back to the pageable copy
-        }
+    if (r->slabRows < 0) {
+        *row0 = 0;
+        *row1 = r->height;
+    } else {
+        *row0 = std::max(0, std::min(r->slabRow0, r->height));
+        *row1 = std::max(*row0, std::min(r->slabRow0 + r->slabRows, r->height));
     }
-    r->lastOutput = output;
 }
 
-// device -> host copy of the whole accumulator after the stream's work
+// device -> host copy of the owned rows of the accumulator after the stream's work.  `output` is
+// the caller's whole-image buffer; whether it is pinned (tb200_pin_output) is the caller's choice:
+// a pageable buffer takes the driver's staged path.
 bool read_back(tb200_renderer* r, float* output)
 {
-    const size_t bytes = size_t(r->width) * r->height * sizeof(float4);
-    pin_output(r, output);
-    TB_CUDA(cudaMemcpyAsync(output, r->boundAccum ? r->boundAccum : r->dAccum, bytes, cudaMemcpyDeviceToHost, r->stream));
+    int row0, row1;
+    owned_rows(r, &row0, &row1);
+    const size_t rowBytes = size_t(r->width) * sizeof(float4);
+    const size_t bytes = size_t(row1 - row0) * rowBytes;
+    const char* accum = (const char*)(r->boundAccum ? r->boundAccum : r->dAccum);
+    if (bytes)
+        TB_CUDA(cudaMemcpyAsync((char*)output + size_t(row0) * rowBytes, accum + size_t(row0) * rowBytes, bytes, cudaMemcpyDeviceToHost, r->stream));
     TB_CUDA(cudaStreamSynchronize(r->stream));
     r->stats.d2hBytes += bytes;
     return true;
@@ -660,12 +691,11 @@ bool read_back(tb200_renderer* r, float* output)
 
 // One frame of the wavefront kernel with the read-back streamed underneath it: samples are handed
 // out in tile-row order, the kernel flags each band of tile rows as its last sample retires
-// (wavefront2.cuh, wf2_band_report), and this thread copies every pixel row that no unfinished
-// sample can still touch while the kernel is tracing the rest.  What is left when the kernel ends
-// is the last band or two instead of the whole W*H*16 bytes.
+// (wavefront2.cuh, wf2_band_report), and this thread copies every owned pixel row that no
+// unfinished sample can still touch while the kernel is tracing the rest.  What is left when the
+// kernel ends is the last band or two instead of the whole slab.
 bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output, bool recordStart = true)
 {
-    pin_output(r, output);
     const float4* accum = P.accum;
     const size_t rowBytes = size_t(r->width) * sizeof(float4);
     // bands of whole tile rows, at most TB_MAX_BANDS, about 256 KiB each: what is left to copy when the
@@ -673,8 +703,9 @@ bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output, bool rec
     int bandTileRows = std::max(1, (int)((size_t(1) << 18) / (rowBytes * 4)));
     bandTileRows = std::max(bandTileRows, (P.tileRows + TB_MAX_BANDS - 1) / TB_MAX_BANDS);
     const int numBands = (P.tileRows + bandTileRows - 1) / bandTileRows;
-    // pixel rows a sample of row y splats into: y - reach .. y + reach (render.cpp:404-407)
-    const int reach = (int)ceilf(std::max(0.0f, P.film.filterWidth)) + 1;
+    const int reach = filter_reach(P.film.filterWidth);
+    int own0, own1;
+    owned_rows(r, &own0, &own1);
 
     r->bandTag += 1;
     if (r->bandTag == 0) r->bandTag = 1;
@@ -686,32 +717,129 @@ bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output, bool rec
     TB_CUDA(cudaMemsetAsync(r->dBandCount, 0, TB_MAX_BANDS * sizeof(unsigned int), r->stream));
     if (!launch_frames(r, P, false)) return false;
 
-    int done = 0;        // bands 0..done-1 are complete
-    int copied = 0;      // pixel rows [0, copied) are already on their way to the host
+    int done = 0;          // bands 0..done-1 are complete
+    int copied = own0;     // owned pixel rows [own0, copied) are already on their way to the host
     bool copyFailed = false;
     auto copy_rows_below = [&](int limit) {
-        limit = std::min(limit, r->height);
+        limit = std::min(limit, own1);
         if (limit <= copied) return;
         if (cudaMemcpyAsync((char*)output + size_t(copied) * rowBytes, (const char*)accum + size_t(copied) * rowBytes,
                             size_t(limit - copied) * rowBytes, cudaMemcpyDeviceToHost, r->copyStream) != cudaSuccess)
             copyFailed = true;
         copied = limit;
     };
+    unsigned spins = 0;
     for (;;) {
         while (done < numBands && r->hBandFlags[done] == r->bandTag) ++done;
         if (done >= numBands) break;
         // unfinished samples sit in local tile rows >= done*bandTileRows, i.e. global pixel rows
-        // >= done*bandTileRows*numShards*4 (decode_sample)
-        copy_rows_below(done * bandTileRows * P.numShards * 4 - reach);
+        // >= firstRow + done*bandTileRows*numShards*4 (decode_sample)
+        copy_rows_below(P.firstRow + done * bandTileRows * P.numShards * 4 - reach);
         if (cudaEventQuery(r->evStop) != cudaErrorNotReady) break;   // finished (or failed): stop polling
-        __builtin_ia32_pause();
+        // back off: the calling thread may be the host application's UI thread (tinsel's GLUT loop)
+        if (++spins < 64u)
+            __builtin_ia32_pause();
+        else
+            std::this_thread::yield();
     }
     TB_CUDA(cudaStreamSynchronize(r->stream));
-    copy_rows_below(r->height);
+    copy_rows_below(own1);
     TB_CUDA(cudaStreamSynchronize(r->copyStream));
     if (copyFailed) TB_CUDA(cudaErrorUnknown);
-    r->stats.d2hBytes += size_t(r->height) * rowBytes;
+    r->stats.d2hBytes += size_t(own1 - own0) * rowBytes;
     return true;
+}
+
+}  // namespace
+
+// One host thread per further device of a multi-device renderer.  Render() is called back to back
+// (16 times per displayed frame, src/main.cpp:242-251) and a frame's kernel takes a fraction of a
+// millisecond, so a worker spins briefly for its next job before it goes to sleep on the condition
+// variable: a wake-up through the kernel would cost as much as the job.
+struct Worker {
+    std::thread thread;
+    std::mutex lock;
+    std::condition_variable wake;
+    std::function<int(tb200_renderer*)> job;
+    std::atomic<uint32_t> posted{0}, done{0};
+    bool sleeping = false, quit = false;
+    int rc = 0;
+};
+
+namespace {
+
+void worker_main(tb200_renderer* r)
+{
+    Worker* w = r->worker;
+    cudaSetDevice(r->device);
+    uint32_t seen = 0;
+    for (;;) {
+        int spins = 0;
+        while (w->posted.load(std::memory_order_acquire) == seen) {
+            if (++spins < 200000) {
+                __builtin_ia32_pause();
+                continue;
+            }
+            std::unique_lock<std::mutex> guard(w->lock);
+            w->sleeping = true;
+            w->wake.wait(guard, [&] { return w->posted.load(std::memory_order_acquire) != seen || w->quit; });
+            w->sleeping = false;
+            if (w->quit) return;
+            spins = 0;
+        }
+        seen += 1;
+        g_error.clear();
+        w->rc = w->job(r);
+        r->workerError = w->rc != 0 ? g_error : std::string();
+        w->done.store(seen, std::memory_order_release);
+    }
+}
+
+void worker_post(tb200_renderer* r, const std::function<int(tb200_renderer*)>& job)
+{
+    Worker* w = r->worker;
+    w->job = job;
+    w->posted.fetch_add(1, std::memory_order_release);
+    std::lock_guard<std::mutex> guard(w->lock);
+    if (w->sleeping) w->wake.notify_one();
+}
+
+int worker_wait(tb200_renderer* r)
+{
+    Worker* w = r->worker;
+    const uint32_t want = w->posted.load(std::memory_order_relaxed);
+    unsigned spins = 0;
+    while (w->done.load(std::memory_order_acquire) != want) {
+        if (++spins < 4096u)
+            __builtin_ia32_pause();
+        else
+            std::this_thread::yield();
+    }
+    return w->rc;
+}
+
+// runs `job` on the head (calling thread) and on every peer (its worker thread) at the same time;
+// returns 0 when all succeeded, else -1 with the first failure as this thread's last error
+int group_run(tb200_renderer* head, const std::function<int(tb200_renderer*)>& job)
+{
+    for (tb200_renderer* p : head->peers) worker_post(p, job);
+    cudaSetDevice(head->device);
+    int rc = job(head);
+    for (tb200_renderer* p : head->peers) {
+        if (worker_wait(p) != 0 && rc == 0) {
+            rc = -1;
+            set_error("device " + std::to_string(p->device) + ": " + p->workerError);
+        }
+    }
+    return rc;
+}
+
+// contiguous row slabs, cut at tile rows (4 pixel rows): member k of n owns [cut(k), cut(k+1))
+int slab_cut(int height, int k, int n)
+{
+    if (k >= n) return height;
+    const int tileRows = (height + 3) / 4;
+    return std::min(height, (int)((long long)tileRows * k / n) * 4);
 }
 
 }  // namespace
@@ -842,19 +970,57 @@ tb200_renderer* tb200_create(const tb200_scene* scene, int device)
     return r;
 }
 
-int tb200_init(tb200_renderer* r, int width, int height)
+tb200_renderer* tb200_create_multi(const tb200_scene* scene, const int* devices, int numDevices)
 {
-    if (!r || width <= 0 || height <= 0) {
-        set_error("tb200_init: bad arguments");
-        return -1;
+    if (!devices || numDevices < 1 || numDevices > TB200_MAX_DEVICES) {
+        set_error("tb200_create_multi: bad device list");
+        return nullptr;
     }
+    for (int a = 0; a < numDevices; ++a)
+        for (int b = 0; b < a; ++b)
+            if (devices[a] == devices[b]) {
+                set_error("tb200_create_multi: a device is listed twice");
+                return nullptr;
+            }
+    // one complete renderer per device (the scene is replicated: SURVEY 8e, at most ~250 MB), built
+    // side by side because most of the time is the host-side re-layout of the meshes
+    std::vector<tb200_renderer*> members(numDevices, nullptr);
+    std::vector<std::string> errors(numDevices);
+    {
+        std::vector<std::thread> builders;
+        for (int k = 0; k < numDevices; ++k)
+            builders.emplace_back([&, k] {
+                members[k] = tb200_create(scene, devices[k]);
+                if (!members[k]) errors[k] = g_error;
+            });
+        for (std::thread& t : builders) t.join();
+    }
+    for (int k = 0; k < numDevices; ++k)
+        if (!members[k]) {
+            set_error("tb200_create_multi: device " + std::to_string(devices[k]) + ": " + errors[k]);
+            for (tb200_renderer* m : members) tb200_destroy(m);
+            return nullptr;
+        }
+    tb200_renderer* head = members[0];
+    for (int k = 1; k < numDevices; ++k) {
+        tb200_renderer* p = members[k];
+        head->peers.push_back(p);
+        // device-to-device gathers go over NVLink when the pair allows peer access
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, p->device, head->device) == cudaSuccess && can) {
+            cudaSetDevice(p->device);
+            if (cudaDeviceEnablePeerAccess(head->device, 0) != cudaSuccess) cudaGetLastError();
+        }
+        p->worker = new Worker();
+        p->worker->thread = std::thread(worker_main, p);
+    }
+    cudaSetDevice(head->device);
+    return head;
+}
+
+static int init_one(tb200_renderer* r, int width, int height)
+{
     cudaSetDevice(r->device);
-    if (r->registered) {
-        cudaHostUnregister(r->registered);   // the caller reallocates its buffer around Init (src/main.cpp:73-88)
-        cudaGetLastError();
-        r->registered = nullptr;
-    }
-    r->lastOutput = nullptr;
     const size_t n = size_t(width) * height;
     if (width != r->width || height != r->height || !r->dAccum) {
         cudaFree(r->dAccum);
@@ -881,18 +1047,37 @@ int tb200_init(tb200_renderer* r, int width, int height)
     return 0;
 }
 
-int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, float* output)
+int tb200_init(tb200_renderer* r, int width, int height)
 {
-    if (!r || !camera || !options || !output) {
-        set_error("tb200_render: null argument");
+    if (!r || width <= 0 || height <= 0) {
+        set_error("tb200_init: bad arguments");
         return -1;
     }
+    if (r->peers.empty()) return init_one(r, width, height);
+    // multi-device: contiguous row slabs cut at tile rows, one per device
+    const int n = (int)r->peers.size() + 1;
+    r->slabRow0 = 0;
+    r->slabRows = slab_cut(height, 1, n);
+    for (int k = 1; k < n; ++k) {
+        r->peers[k - 1]->slabRow0 = slab_cut(height, k, n);
+        r->peers[k - 1]->slabRows = slab_cut(height, k + 1, n) - slab_cut(height, k, n);
+    }
+    return group_run(r, [=](tb200_renderer* m) { return init_one(m, width, height); });
+}
+
+static int render_one(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, float* output)
+{
     cudaSetDevice(r->device);
-    if (options->mode == TB200_MODE_COMPLEXITY) return 0;   // render.cpp:516-519
     LaunchParams P;
     if (!fill_params(r, camera, options, &P)) return -1;
     if (options->mode == TB200_MODE_NORMALS) {
         unsigned long long launches = 0;
+        if (r->slabRows >= 0) {
+            // eNormals writes each pixel from its own primary ray: the owned rows, no halo
+            P.firstRow = P.film.rowLo;
+            P.numRows = P.film.rowHi - P.film.rowLo;
+            finalize_params(&P);
+        }
         cudaEventRecord(r->evStart, r->stream);
         launch_normals(P, r->stream, &launches);
         cudaEventRecord(r->evStop, r->stream);
@@ -924,13 +1109,21 @@ int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     return 0;
 }
 
-int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int spp,
-                        int firstRow, int numRows)
+int tb200_render(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, float* output)
 {
-    if (!r || !camera || !options || spp < 0) {
-        set_error("tb200_render_device: bad argument");
+    if (!r || !camera || !options || !output) {
+        set_error("tb200_render: null argument");
         return -1;
     }
+    if (options->mode == TB200_MODE_COMPLEXITY) return 0;   // render.cpp:516-519
+    if (r->peers.empty()) return render_one(r, camera, options, output);
+    // every device traces its slab and streams its own rows into `output` over its own PCIe link
+    return group_run(r, [=](tb200_renderer* m) { return render_one(m, camera, options, output); });
+}
+
+static int render_device_one(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int spp,
+                             int firstRow, int numRows)
+{
     cudaSetDevice(r->device);
     if (options->mode != TB200_MODE_PATHTRACE) {
         set_error("tb200_render_device: only ePathTrace is batched");
@@ -939,6 +1132,10 @@ int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb2
     LaunchParams P;
     if (!fill_params(r, camera, options, &P)) return -1;
     if (numRows >= 0) {
+        if (r->slabRows >= 0) {
+            set_error("tb200_render_device: a row range cannot be combined with a row slab (tb200_set_slab / multi-device)");
+            return -1;
+        }
         if (firstRow < 0 || firstRow + numRows > options->height) {
             set_error("tb200_render_device: row range outside the image");
             return -1;
@@ -958,26 +1155,94 @@ int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb2
     return 0;
 }
 
+int tb200_render_device(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int spp,
+                        int firstRow, int numRows)
+{
+    if (!r || !camera || !options || spp < 0) {
+        set_error("tb200_render_device: bad argument");
+        return -1;
+    }
+    if (r->peers.empty()) return render_device_one(r, camera, options, spp, firstRow, numRows);
+    return group_run(r, [=](tb200_renderer* m) { return render_device_one(m, camera, options, spp, firstRow, numRows); });
+}
+
+#define TB_SINGLE_DEVICE_ONLY(r, what)                                                              \
+    if (!(r)->peers.empty()) {                                                                      \
+        set_error(what ": not available on a multi-device renderer");                               \
+        return -1;                                                                                  \
+    }
+
 int tb200_set_shard(tb200_renderer* r, int shard, int numShards)
 {
     if (!r || numShards < 1 || shard < 0 || shard >= numShards) {
         set_error("tb200_set_shard: bad arguments");
         return -1;
     }
+    TB_SINGLE_DEVICE_ONLY(r, "tb200_set_shard")
     r->shard = shard;
     r->numShards = numShards;
     return 0;
 }
 
-int tb200_set_stream(tb200_renderer* r, void* cudaStream)
+int tb200_set_stream(tb200_renderer* r, void* cudaStream, int external)
 {
     if (!r) {
         set_error("tb200_set_stream: null renderer");
         return -1;
     }
+    TB_SINGLE_DEVICE_ONLY(r, "tb200_set_stream")
     cudaSetDevice(r->device);
     cudaStreamSynchronize(r->stream);
-    r->stream = cudaStream ? (cudaStream_t)cudaStream : r->ownStream;
+    // handle 0 with external != 0 is CUDA's legacy default stream, a perfectly good caller stream
+    r->stream = external ? (cudaStream_t)cudaStream : r->ownStream;
+    return 0;
+}
+
+int tb200_set_slab(tb200_renderer* r, int firstRow, int numRows)
+{
+    if (!r || (numRows >= 0 && firstRow < 0)) {
+        set_error("tb200_set_slab: bad arguments");
+        return -1;
+    }
+    TB_SINGLE_DEVICE_ONLY(r, "tb200_set_slab")
+    if (numRows >= 0 && r->numShards > 1) {
+        set_error("tb200_set_slab: cannot be combined with tb200_set_shard");
+        return -1;
+    }
+    r->slabRow0 = numRows >= 0 ? firstRow : 0;
+    r->slabRows = numRows >= 0 ? numRows : -1;
+    return 0;
+}
+
+int tb200_pin_output(tb200_renderer* r, float* output, size_t bytes)
+{
+    if (!r || !output || bytes == 0) {
+        set_error("tb200_pin_output: bad arguments");
+        return -1;
+    }
+    cudaSetDevice(r->device);
+    if (r->registered == output && r->registeredBytes == bytes) return 0;
+    if (r->registered) tb200_unpin_output(r);
+    // portable: every device of a multi-device renderer copies its rows straight into this buffer
+    if (cudaHostRegister(output, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        set_error(std::string("tb200_pin_output: cudaHostRegister: ") + cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    r->registered = output;
+    r->registeredBytes = bytes;
+    return 0;
+}
+
+int tb200_unpin_output(tb200_renderer* r)
+{
+    if (!r) return -1;
+    if (r->registered) {
+        cudaSetDevice(r->device);
+        cudaHostUnregister(r->registered);
+        cudaGetLastError();
+        r->registered = nullptr;
+        r->registeredBytes = 0;
+    }
     return 0;
 }
 
@@ -987,6 +1252,7 @@ int tb200_bind_accumulator(tb200_renderer* r, float* deviceAccum)
         set_error("tb200_bind_accumulator: call tb200_init first");
         return -1;
     }
+    TB_SINGLE_DEVICE_ONLY(r, "tb200_bind_accumulator")
     r->boundAccum = (float4*)deviceAccum;
     return 0;
 }
@@ -1003,21 +1269,47 @@ int tb200_read_accumulator(tb200_renderer* r, float* output)
         set_error("tb200_read_accumulator: bad argument");
         return -1;
     }
-    cudaSetDevice(r->device);
-    return read_back(r, output) ? 0 : -1;
+    return group_run(r, [=](tb200_renderer* m) {
+        cudaSetDevice(m->device);
+        return read_back(m, output) ? 0 : -1;
+    });
 }
 
-int tb200_render_n(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int n, float* output)
+int tb200_gather_device(tb200_renderer* r)
 {
-    if (!r || !camera || !options || !output || n < 1) {
-        set_error("tb200_render_n: bad argument");
+    if (!r || !r->dAccum) {
+        set_error("tb200_gather_device: call tb200_init first");
         return -1;
+    }
+    // every peer's slab -> the head's accumulator, device to device (NVLink when peer access is on)
+    const size_t rowBytes = size_t(r->width) * sizeof(float4);
+    for (tb200_renderer* p : r->peers) {
+        int row0, row1;
+        owned_rows(p, &row0, &row1);
+        if (row1 <= row0) continue;
+        cudaSetDevice(p->device);
+        if (cudaMemcpyPeerAsync((char*)r->dAccum + size_t(row0) * rowBytes, r->device, (const char*)p->dAccum + size_t(row0) * rowBytes,
+                                p->device, size_t(row1 - row0) * rowBytes, p->stream) != cudaSuccess) {
+            set_error(std::string("tb200_gather_device: ") + cudaGetErrorString(cudaGetLastError()));
+            return -1;
+        }
+    }
+    for (tb200_renderer* p : r->peers) {
+        cudaSetDevice(p->device);
+        if (cudaStreamSynchronize(p->stream) != cudaSuccess) {
+            set_error(std::string("tb200_gather_device: ") + cudaGetErrorString(cudaGetLastError()));
+            return -1;
+        }
     }
     cudaSetDevice(r->device);
-    if (options->mode != TB200_MODE_PATHTRACE) {
-        set_error("tb200_render_n: only ePathTrace is batched");
-        return -1;
-    }
+    return 0;
+}
+
+int tb200_num_devices(const tb200_renderer* r) { return r ? (int)r->peers.size() + 1 : 0; }
+
+static int render_n_one(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int n, float* output)
+{
+    cudaSetDevice(r->device);
     LaunchParams P;
     if (!fill_params(r, camera, options, &P)) return -1;
     // frames k .. k+n-2 in one launch, the last one with the read-back streamed underneath it
@@ -1045,6 +1337,20 @@ int tb200_render_n(tb200_renderer* r, const tb200_camera* camera, const tb200_op
     return 0;
 }
 
+int tb200_render_n(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int n, float* output)
+{
+    if (!r || !camera || !options || !output || n < 1) {
+        set_error("tb200_render_n: bad argument");
+        return -1;
+    }
+    if (options->mode != TB200_MODE_PATHTRACE) {
+        set_error("tb200_render_n: only ePathTrace is batched");
+        return -1;
+    }
+    if (r->peers.empty()) return render_n_one(r, camera, options, n, output);
+    return group_run(r, [=](tb200_renderer* m) { return render_n_one(m, camera, options, n, output); });
+}
+
 int tb200_finish(tb200_renderer* r, float exposure, float limit, float* filtered, unsigned char* rgb8)
 {
     (void)limit;   // ToneMap's filmic branch ignores it (util.h:25-42), kept for the call shape of main.cpp:269
@@ -1052,6 +1358,7 @@ int tb200_finish(tb200_renderer* r, float exposure, float limit, float* filtered
         set_error("tb200_finish: tb200_init has not been called");
         return -1;
     }
+    if (!r->peers.empty() && tb200_gather_device(r) != 0) return -1;   // the finish step runs on the head device
     cudaSetDevice(r->device);
     const int W = r->width, H = r->height;
     const size_t n = size_t(W) * H;
@@ -1187,7 +1494,14 @@ int tb200_trace_frame(tb200_renderer* r, const tb200_camera* camera, const tb200
     }
     cudaSetDevice(r->device);
     LaunchParams P;
-    if (!fill_params(r, camera, options, &P)) return -1;
+    {
+        // a probe of the whole frame on this device, whatever slab it owns when rendering
+        const int slabRows = r->slabRows;
+        r->slabRows = -1;
+        const bool ok = fill_params(r, camera, options, &P);
+        r->slabRows = slabRows;
+        if (!ok) return -1;
+    }
     const size_t n = size_t(r->width) * r->height;
     if (!r->dRadiance) {
         if (cudaMalloc((void**)&r->dRadiance, n * 3 * sizeof(float)) != cudaSuccess ||
@@ -1200,6 +1514,12 @@ int tb200_trace_frame(tb200_renderer* r, const tb200_camera* camera, const tb200
     P.numFrames = 1;
     P.outRadiance = r->dRadiance;
     P.outRaster = r->dRaster;
+    // pixels of other shards (tb200_set_shard) are not traced by this renderer: they read back as zero
+    if (cudaMemsetAsync(r->dRadiance, 0, n * 3 * sizeof(float), r->stream) != cudaSuccess ||
+        cudaMemsetAsync(r->dRaster, 0, n * 2 * sizeof(float), r->stream) != cudaSuccess) {
+        set_error("tb200_trace_frame: scratch clear failed");
+        return -1;
+    }
     const uint64_t samplesBefore = r->stats.samples;
     if (!launch_frames(r, P)) return -1;
     r->stats.samples = samplesBefore;
@@ -1215,17 +1535,41 @@ int tb200_trace_frame(tb200_renderer* r, const tb200_camera* camera, const tb200
 
 void tb200_set_frame(tb200_renderer* r, int frame)
 {
-    if (r) r->frame = frame;
+    if (!r) return;
+    r->frame = frame;
+    for (tb200_renderer* p : r->peers) p->frame = frame;
 }
 
 void tb200_get_stats(tb200_renderer* r, tb200_stats* out)
 {
-    if (r && out) *out = r->stats;
+    if (!r || !out) return;
+    *out = r->stats;
+    for (const tb200_renderer* p : r->peers) {
+        out->samples += p->stats.samples;
+        out->kernelLaunches += p->stats.kernelLaunches;
+        out->d2hBytes += p->stats.d2hBytes;
+        out->h2dBytes += p->stats.h2dBytes;
+        out->gpuMs = std::max(out->gpuMs, p->stats.gpuMs);
+    }
 }
 
 void tb200_destroy(tb200_renderer* r)
 {
     if (!r) return;
+    for (tb200_renderer* p : r->peers) tb200_destroy(p);
+    r->peers.clear();
+    if (r->worker) {
+        {
+            std::lock_guard<std::mutex> guard(r->worker->lock);
+            r->worker->quit = true;
+        }
+        r->worker->posted.fetch_add(1, std::memory_order_release);   // leave the spin, see `quit`
+        r->worker->wake.notify_one();
+        if (r->worker->thread.joinable()) r->worker->thread.join();
+        delete r->worker;
+        r->worker = nullptr;
+    }
+    tb200_unpin_output(r);
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
     free_device(r);

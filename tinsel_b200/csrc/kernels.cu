@@ -124,7 +124,10 @@ __global__ void __launch_bounds__(128) k_normals(LaunchParams P)
     const int W = P.film.width;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P.numRows * W) return;
-    const int py = P.firstRow + idx / W;
+    const int ry = idx / W;
+    // image-plane shards own the 4-row tile rows t with t % numShards == shard (decode_sample)
+    if ((ry >> 2) % P.numShards != P.shard) return;
+    const int py = P.firstRow + ry;
     const int px = idx % W;
     V3 origin, dir;
     generate_ray(P.camera, (float)px, (float)py, origin, dir);

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -93,14 +95,21 @@ static bool read_exact(FILE* f, void* dst, size_t bytes)
     return bytes == 0 || fread(dst, 1, bytes, f) == bytes;
 }
 
-extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
+// bytes left between the read position and the end of the file (counts are checked against it before
+// any array is sized from them, as tb200_mesh_bin_load does: a corrupt header must not turn into a
+// bad_alloc thrown through the C ABI)
+static uint64_t bytes_left(FILE* f)
 {
-    FILE* f = fopen(path, "rb");
-    if (!f) {
-        snap_error(std::string("cannot open snapshot ") + path);
-        return nullptr;
-    }
-    tb200_snapshot* s = new tb200_snapshot();
+    const long here = ftell(f);
+    if (here < 0 || fseek(f, 0, SEEK_END) != 0) return 0;
+    const long end = ftell(f);
+    fseek(f, here, SEEK_SET);
+    return end > here ? uint64_t(end - here) : 0;
+}
+
+static tb200_snapshot* snapshot_load_impl(FILE* f)
+{
+    std::unique_ptr<tb200_snapshot> s(new tb200_snapshot());   // freed if a resize throws
     bool ok = true;
     char magic[8];
     uint32_t hdr[6];
@@ -110,6 +119,11 @@ extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
     ok = ok && read_exact(f, &s->options, sizeof(tb200_options));
     float sky[6];
     ok = ok && read_exact(f, sky, sizeof(sky));
+    if (ok) {
+        const uint64_t left = bytes_left(f);
+        ok = uint64_t(hdr[0]) * sizeof(tb200_primitive) + uint64_t(hdr[2]) * sizeof(tb200_bvh_node) +
+                 uint64_t(hdr[1]) * 16u <= left;
+    }
     if (ok) {
         s->primitives.resize(hdr[0]);
         s->bvhNodes.resize(hdr[2]);
@@ -122,6 +136,10 @@ extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
             float area;
             ok = ok && read_exact(f, counts, sizeof(counts)) && read_exact(f, &area, 4);
             if (!ok) break;
+            if (counts[0] < 0 || counts[1] < 0 || counts[2] < 0) { ok = false; break; }
+            const uint64_t need = uint64_t(counts[0]) * 24u + uint64_t(counts[1]) * 4u +
+                                  uint64_t(counts[2]) * sizeof(tb200_bvh_node) + uint64_t(counts[1]) / 3u * 4u;
+            if (need > bytes_left(f)) { ok = false; break; }
             MeshStore& d = s->meshData[m];
             d.positions.resize(size_t(counts[0]) * 3);
             d.normals.resize(size_t(counts[0]) * 3);
@@ -147,8 +165,10 @@ extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
     }
     memset(&s->scene, 0, sizeof(s->scene));
     if (ok && hdr[3]) {
-        const size_t n = size_t(hdr[4]) * hdr[5];
-        std::vector<float> rgb(n * 3);
+        const uint64_t n64 = uint64_t(hdr[4]) * hdr[5];
+        ok = n64 > 0 && n64 * 12u <= bytes_left(f);
+        const size_t n = size_t(n64);
+        std::vector<float> rgb(ok ? n * 3 : 0);
         ok = ok && read_exact(f, rgb.data(), rgb.size() * 4);
         if (ok) {
             s->probeData.assign((n + 1) * 4, 0.0f);
@@ -158,7 +178,7 @@ extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
                 s->probeData[i * 4 + 2] = rgb[i * 3 + 2];
                 s->probeData[i * 4 + 3] = 0.0f;  // Color(r,g,b): w defaults to 0 (src/maths.h:292)
             }
-            build_probe_tables(s, int(hdr[4]), int(hdr[5]));
+            build_probe_tables(s.get(), int(hdr[4]), int(hdr[5]));
             s->scene.sky.probeValid = 1;
             s->scene.sky.probeWidth = int(hdr[4]);
             s->scene.sky.probeHeight = int(hdr[5]);
@@ -169,12 +189,7 @@ extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
             s->scene.sky.cdfValuesY = s->cdfY.data();
         }
     }
-    fclose(f);
-    if (!ok) {
-        snap_error(std::string("truncated or malformed snapshot ") + path);
-        delete s;
-        return nullptr;
-    }
+    if (!ok) return nullptr;
     memcpy(s->scene.sky.horizon, sky, 12);
     memcpy(s->scene.sky.zenith, sky + 3, 12);
     s->scene.primitives = s->primitives.data();
@@ -183,6 +198,26 @@ extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
     s->scene.numMeshes = int32_t(s->meshes.size());
     s->scene.bvhNodes = s->bvhNodes.data();
     s->scene.numBvhNodes = int32_t(s->bvhNodes.size());
+    return s.release();
+}
+
+extern "C" tb200_snapshot* tb200_snapshot_load(const char* path)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        snap_error(std::string("cannot open snapshot ") + path);
+        return nullptr;
+    }
+    tb200_snapshot* s = nullptr;
+    try {
+        s = snapshot_load_impl(f);   // no exception may cross the C ABI
+    } catch (const std::exception& e) {
+        fclose(f);
+        snap_error(std::string("snapshot ") + path + ": " + e.what());
+        return nullptr;
+    }
+    fclose(f);
+    if (!s) snap_error(std::string("truncated or malformed snapshot ") + path);
     return s;
 }
 

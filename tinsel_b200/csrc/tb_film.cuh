@@ -19,6 +19,10 @@ struct DFilm {
     // arguments below this give expf(arg) < offset by a wide margin, i.e. Gaussian() == +0 exactly
     // (host: log(offset*(1-1e-3)); -inf disables the shortcut)
     float filterArgZero;
+    // Owner-computes row slabs (multi-GPU): splats land only in pixel rows [rowLo, rowHi).  A device
+    // that owns a slab also traces the samples of the rows within the filter's reach outside it, so
+    // its rows receive exactly the contributions the whole image would give them.  Default: all rows.
+    int rowLo, rowHi;
 };
 
 // GenerateRay, util.h:73-79 with TransformPoint(Mat44, Vec3(x,y,0)), maths.h:923-930
@@ -53,9 +57,9 @@ TB_DEV void accum_add(float4* accum, int idx, float r, float g, float b, float w
 TB_DEV void add_sample(const DFilm& f, float4* accum, float rasterX, float rasterY, V3 sample)
 {
     const int startX = tb_max(0, int(rasterX - f.filterWidth));
-    const int startY = tb_max(0, int(rasterY - f.filterWidth));
+    const int startY = tb_max(f.rowLo, int(rasterY - f.filterWidth));
     const int endX = tb_min(int(rasterX + f.filterWidth), f.width - 1);
-    const int endY = tb_min(int(rasterY + f.filterWidth), f.height - 1);
+    const int endY = tb_min(int(rasterY + f.filterWidth), f.rowHi - 1);
 
     // ClampLength, maths.h:1577-1589
     V3 c = sample;

@@ -33,6 +33,8 @@
 // second trace queue for rays that enter a big mesh.
 #pragma once
 
+#include <mutex>
+
 #ifndef TB_WF2_THREADS
 #define TB_WF2_THREADS 512
 #endif
@@ -687,18 +689,32 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     }
 }
 
+// The opt-in to > 48 KB of dynamic shared memory and the occupancy answer are PER DEVICE (and the
+// attribute applies to the current device only), so they are kept per device ordinal and set up once
+// per device under a lock: a host may own renderers on several GPUs, driven from several threads.
+#define TB_WF2_MAX_DEVICES 64
+template <int THREADS, int MODE>
+static int wavefront2_ctas_per_sm()
+{
+    static std::mutex lock;
+    static int ctasPerSM[TB_WF2_MAX_DEVICES] = {};   // 0 = not configured yet
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TB_WF2_MAX_DEVICES) dev = 0;
+    std::lock_guard<std::mutex> guard(lock);
+    if (ctasPerSM[dev] == 0) {
+        int n = 0;
+        cudaFuncSetAttribute(k_wavefront2<THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wf2Shared));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront2<THREADS, MODE>, THREADS, sizeof(Wf2Shared)) != cudaSuccess || n < 1)
+            n = 1;
+        ctasPerSM[dev] = n;
+    }
+    return ctasPerSM[dev];
+}
+
 template <int THREADS, int MODE>
 static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long total)
 {
-    static bool configured = false;
-    static int ctasPerSM = 0;
-    if (!configured) {
-        cudaFuncSetAttribute(k_wavefront2<THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wf2Shared));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, k_wavefront2<THREADS, MODE>, THREADS, sizeof(Wf2Shared)) != cudaSuccess ||
-            ctasPerSM < 1)
-            ctasPerSM = 1;
-        configured = true;
-    }
+    const int ctasPerSM = wavefront2_ctas_per_sm<THREADS, MODE>();
     // TB_WF2_CTAS_PER_SM resident CTAs per SM; small jobs use fewer so that every CTA has a full slot array
     const unsigned long long want = (total + TB_WF2_PATHS - 1) / TB_WF2_PATHS;
     int grid = (numSMs > 0 ? numSMs : 148) * ctasPerSM;

@@ -115,16 +115,45 @@ struct GpuWavefrontRenderer : public Renderer {
             xs.sky.pdfValuesY = pr.pdfValuesY;
             xs.sky.cdfValuesY = pr.cdfValuesY;
         }
+        // Options cannot change (render.h:50-63), so renderer-private knobs are environment variables:
+        //   TINSEL_GPUS=N          spread the renderer over CUDA devices 0..N-1 of this box (row slabs,
+        //                          every GPU copies its own rows to the host; tb200_create_multi)
+        //   TINSEL_B200_DEVICE=k   single-device ordinal (default 0)
+        //   TINSEL_B200_PIN=0      never page-lock the caller's frame buffer (see Render below)
         const char* dev = getenv("TINSEL_B200_DEVICE");
-        impl = tb200_create(&xs, dev ? atoi(dev) : 0);
+        const char* gpus = getenv("TINSEL_GPUS");
+        const int n = gpus ? atoi(gpus) : 1;
+        if (n > 1) {
+            std::vector<int> devices;
+            for (int k = 0; k < n; ++k) devices.push_back(k);
+            impl = tb200_create_multi(&xs, devices.data(), n);
+        } else {
+            impl = tb200_create(&xs, dev ? atoi(dev) : 0);
+        }
+        const char* pin = getenv("TINSEL_B200_PIN");
+        allowPin = !(pin && atoi(pin) == 0);
         if (!impl) fprintf(stderr, "CreateGpuWavefrontRenderer: %s\n", tb200_last_error());
     }
 
-    ~GpuWavefrontRenderer() override { tb200_destroy(impl); }
+    ~GpuWavefrontRenderer() override { tb200_destroy(impl); }   // unpins
+
+    // Frame-buffer pinning.  The C ABI never page-locks caller memory by itself; this adapter does, on
+    // the strength of tinsel's own contract for `output`: main.cpp owns ONE frame buffer, g_pixels,
+    // passes it to every Render() (main.cpp:249) and reallocates it only in InitFrameBuffer(), which
+    // calls Init() straight afterwards (main.cpp:73-88) and before any further Render().  So: a buffer
+    // seen in two consecutive Render() calls is pinned; Init() -- the one notification a reallocation
+    // produces -- unpins; a Render() with a different pointer unpins first.  Between the application's
+    // delete[] and its Init() call the stale registration is never used for a copy.
+    bool allowPin = true;
+    Color* lastOutput = nullptr;
+    Color* pinned = nullptr;
 
     void Init(int width, int height) override
     {
-        if (impl && tb200_init(impl, width, height) != 0) fprintf(stderr, "GpuWavefrontRenderer::Init: %s\n", tb200_last_error());
+        if (!impl) return;
+        tb200_unpin_output(impl);
+        pinned = lastOutput = nullptr;
+        if (tb200_init(impl, width, height) != 0) fprintf(stderr, "GpuWavefrontRenderer::Init: %s\n", tb200_last_error());
     }
 
     // The reference has no error channel (void, no exceptions): failures are logged, `output` is
@@ -132,6 +161,14 @@ struct GpuWavefrontRenderer : public Renderer {
     void Render(const Camera& c, const Options& options, Color* output) override
     {
         if (!impl) return;
+        if (pinned && pinned != output) {
+            tb200_unpin_output(impl);
+            pinned = nullptr;
+        }
+        if (allowPin && !pinned && output == lastOutput &&
+            tb200_pin_output(impl, reinterpret_cast<float*>(output), size_t(options.width) * options.height * sizeof(Color)) == 0)
+            pinned = output;
+        lastOutput = output;
         const tb200_camera* xc = reinterpret_cast<const tb200_camera*>(&c);      // identical layouts (static_assert above)
         const tb200_options* xo = reinterpret_cast<const tb200_options*>(&options);
         if (tb200_render(impl, xc, xo, reinterpret_cast<float*>(output)) != 0)

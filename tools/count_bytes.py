@@ -56,16 +56,15 @@ if __name__ == "__main__":
     scene = sys.argv[1] if len(sys.argv) > 1 else "cornell"
     w = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
     h = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
-    spp = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+    spp = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4].isdigit() else 2
     res = count(scene, w, h, spp)
     print(json.dumps(res, indent=1))
-    if scene == "cornell" and (w, h) == (1024, 1024):
+    if "--write" in sys.argv:
+        # merge into tools/algo_bytes.json (bench.py reads it); the ncu-derived constants of the entry stay
         out = os.path.join(ROOT, "tools", "algo_bytes.json")
-        old = {}
-        if os.path.exists(out):
-            old = json.load(open(out))
-        res["dram_traffic_bytes_per_launch"] = old.get("dram_traffic_bytes_per_launch")
-        res["dram_traffic_source"] = old.get("dram_traffic_source")
-        res["other_scenes"] = old.get("other_scenes")
-        json.dump(res, open(out, "w"), indent=1)
+        doc = json.load(open(out)) if os.path.exists(out) else {"scenes": {}}
+        entry = doc["scenes"].setdefault(scene, {})
+        entry.update({"counted_at": "%dx%d, %d spp" % (w, h, spp), "per_sample": res["per_sample"],
+                      "traversal_bytes_per_sample": res["traversal_bytes_per_sample"], "bytes_per_sample": res["bytes_per_sample"]})
+        json.dump(doc, open(out, "w"), indent=1)
         print("wrote", out)
