@@ -175,6 +175,14 @@ tb200_renderer* tb200_create(const tb200_scene* scene, int device);
 tb200_renderer* tb200_create_multi(const tb200_scene* scene, const int* devices, int numDevices);
 int tb200_num_devices(const tb200_renderer* r);
 
+/* The slab rule tb200_init applies to a multi-device renderer, for hosts that run one process per GPU
+ * and call tb200_set_slab themselves: member k of n owns pixel rows [*firstRow, *firstRow + *numRows)
+ * (contiguous, cut at 4-row tile rows).  tb200_slab_traced_rows: the rows whose samples the owner of
+ * [firstRow, firstRow+numRows) traces -- the slab plus the filter's reach (ceil(width)+1 rows,
+ * render.cpp:404-407) on either side, clipped to the image. */
+void tb200_slab_rows(int height, int member, int numMembers, int* firstRow, int* numRows);
+void tb200_slab_traced_rows(int height, int firstRow, int numRows, float filterWidth, int* firstTraced, int* numTraced);
+
 /* Replaces Renderer::Init (src/render.h:70; semantics of src/render.cu:1070-1075):
  * (re)allocates and zeroes the device accumulator, resets the frame counter. Returns 0 on success. */
 int tb200_init(tb200_renderer* r, int width, int height);

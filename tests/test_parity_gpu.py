@@ -213,29 +213,35 @@ def test_max_depth_edge_cases(depth, pipeline):
 
 
 @pytest.mark.parametrize("cta", ["512", "768"])
-@pytest.mark.parametrize("sched", ["hard", "free", "split"])
+@pytest.mark.parametrize("sched", ["hard", "free", "split", "offload", "offload1", "offload100"])
 def test_both_scheduling_modes_bit_exact(sched, cta):
     """Every scheduler variant x CTA size of the wavefront kernel (the per-scene heuristics of
-    api.cu build_scene pick one of them) produces the same bits: hard phases, free running, and
-    free running with the split trace queue forced on for every scene that has a mesh."""
-    os.environ["TINSEL_B200_SCHED"] = "free" if sched == "split" else sched
+    api.cu build_scene pick one of them) produces the same bits: hard phases, free running, free
+    running with the split trace queue forced on for every scene that has a mesh, and the mesh-walk
+    offload (shader CTAs + walker CTAs, wavefront_walk.cuh) forced on for every mesh, with the
+    default number of walker CTAs, a single one, and as many as fit."""
+    offload = sched.startswith("offload")
+    os.environ["TINSEL_B200_SCHED"] = "free" if sched == "split" or offload else sched
     os.environ["TINSEL_B200_SPLIT"] = "1" if sched == "split" else "0"
+    os.environ["TINSEL_B200_OFFLOAD"] = "1" if offload else "0"
+    if sched in ("offload1", "offload100"):
+        os.environ["TINSEL_B200_WALKERS"] = sched[len("offload"):]
     os.environ["TINSEL_B200_CTA"] = cta
     try:
-        for name in ("veach", "meshlight", "many", "envmini", "glass", "table", "ajax"):
+        for name in ("veach", "meshlight", "many", "envmini", "glass", "table", "ajax", "motionblur"):
             if not _available(name):
                 continue
             snap, cam, opt, ref, r = _setup(name, "wavefront")
-            rad, _ = r.trace_frame(cam, opt, 3)
-            rrad, _ = ref.trace_frame(3, nthreads=8)
-            assert (rad.view(np.uint32) == rrad.view(np.uint32)).all(), name
+            for frame in (3, 4):   # two launches: the offload queues' counters and lap tags run on across launches
+                rad, _ = r.trace_frame(cam, opt, frame)
+                rrad, _ = ref.trace_frame(frame, nthreads=8)
+                assert (rad.view(np.uint32) == rrad.view(np.uint32)).all(), (name, frame)
             r.close()
             ref.close()
             snap.close()
     finally:
-        os.environ.pop("TINSEL_B200_SCHED", None)
-        os.environ.pop("TINSEL_B200_SPLIT", None)
-        os.environ.pop("TINSEL_B200_CTA", None)
+        for k in ("TINSEL_B200_SCHED", "TINSEL_B200_SPLIT", "TINSEL_B200_CTA", "TINSEL_B200_OFFLOAD", "TINSEL_B200_WALKERS"):
+            os.environ.pop(k, None)
 
 
 def test_box_filter_and_clamp():
@@ -345,6 +351,52 @@ def test_baseline_configs_full_size(name, size):
     num = np.linalg.norm((out - oracle).astype(np.float64))
     den = np.linalg.norm(oracle.astype(np.float64))
     assert num / den <= 1e-4, "rel L2 %g" % (num / den)
+    r.close()
+    ref.close()
+    snap.close()
+
+
+# north_star's tolerance is against src/render.cpp AS SHIPPED (glibc libm, `flavour="literal"`:
+# render.cpp:230-388 compiled unmodified), not against the deterministic-libm pin used above.  Per-sample
+# exactness is impossible there in principle (glibc's sinf/cosf/expf/acosf/atan2f differ from the
+# correctly rounded results in the last bit for 0.06-16 % of arguments), so: the image at matched
+# seeds and spp must agree to rel-L2 <= 1e-4 on every BASELINE.json GPU configuration at its full
+# size, and the per-sample differences are counted and printed (last-bit differences vs. flipped paths).
+LITERAL_REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "literal_parity.txt")
+
+
+@pytest.mark.parametrize("name,size", [("cornell", (1024, 1024)), ("ajax", (1024, 1024)), ("veach", (1920, 1080)),
+                                       ("env", (2048, 2048)), ("glass", (512, 512))])
+def test_literal_reference_rel_l2_at_baseline_sizes(name, size):
+    snap, cam, opt, ref, r = _setup(name, "wavefront", size=size, flavour="literal")
+    threads = os.cpu_count() or 8
+    spp = 8
+    out = np.zeros((opt.height, opt.width, 4), np.float32)
+    r.render_n(cam, opt, spp, out)
+    oracle = ref.render_pool(0, spp, threads)
+    num = np.linalg.norm((out - oracle).astype(np.float64))
+    den = np.linalg.norm(oracle.astype(np.float64))
+    # normalised image (rgb / w), the quantity main.cpp displays
+    wgt = np.maximum(oracle[..., 3:], 1e-20)
+    img_o, img_g = oracle[..., :3] / wgt, out[..., :3] / np.maximum(out[..., 3:], 1e-20)
+    rel_img = np.linalg.norm((img_g - img_o).astype(np.float64)) / np.linalg.norm(img_o.astype(np.float64))
+    # per-sample bookkeeping on one frame
+    rad, _ = r.trace_frame(cam, opt, 1)
+    rrad, _ = ref.trace_frame(1, nthreads=threads)
+    same = (rad.view(np.uint32) == rrad.view(np.uint32)).all(-1)
+    mag = np.maximum(np.abs(rrad).max(-1), 1e-6)
+    flipped = (np.abs(rad - rrad).max(-1) / mag) > 1e-3
+    msg = "%-8s %4dx%-4d %d spp: rel-L2 sums %.3e, rel-L2 rgb/w %.3e; frame 1: %d of %d samples differ in the last bits, %d by more than 1e-3 (flipped paths)" % (
+        name, size[0], size[1], spp, num / den, rel_img, int((~same).sum()), same.size, int(flipped.sum()))
+    print(msg)
+    try:
+        os.makedirs(os.path.dirname(LITERAL_REPORT), exist_ok=True)
+        with open(LITERAL_REPORT, "a") as f:
+            f.write(msg + "\n")
+    except OSError:
+        pass
+    assert num / den <= 1e-4, msg
+    assert rel_img <= 1e-4, msg
     r.close()
     ref.close()
     snap.close()

@@ -54,6 +54,10 @@ def load_library():
     lib.tb200_create_multi.argtypes = [C.POINTER(Scene), C.POINTER(C.c_int), C.c_int]
     lib.tb200_num_devices.restype = C.c_int
     lib.tb200_num_devices.argtypes = [C.c_void_p]
+    lib.tb200_slab_rows.restype = None
+    lib.tb200_slab_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.tb200_slab_traced_rows.restype = None
+    lib.tb200_slab_traced_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.tb200_set_slab.restype = C.c_int
     lib.tb200_set_slab.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.tb200_pin_output.restype = C.c_int

@@ -152,6 +152,8 @@ EXPORTS = [
     "tb200_create",
     "tb200_create_multi",
     "tb200_num_devices",
+    "tb200_slab_rows",
+    "tb200_slab_traced_rows",
     "tb200_set_slab",
     "tb200_pin_output",
     "tb200_unpin_output",

@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libtinsel_b200.so")
 
 SOURCES = ["kernels.cu", "api.cu", "snapshot.cpp"]
-HEADERS = ["tb_math.cuh", "tb_scene.cuh", "tb_shade.cuh", "tb_film.cuh", "tb_kernels.cuh", "wavefront2.cuh"]
+HEADERS = ["tb_math.cuh", "tb_scene.cuh", "tb_shade.cuh", "tb_film.cuh", "tb_kernels.cuh", "wavefront2.cuh", "wavefront_walk.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

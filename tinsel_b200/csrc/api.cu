@@ -111,23 +111,47 @@ DMaterial make_material(const tb200_material& m)
     return d;
 }
 
-// BVHNode[] (bvh.h:9-19) -> BvhPair[]; see tb_scene.cuh.  Returns the root reference.
-uint32_t build_pairs(const tb200_bvh_node* nodes, int numNodes, std::vector<BvhPair>* out)
+// BVHNode[] (bvh.h:9-19) -> BvhPair[]; see tb_scene.cuh.  Returns the root reference.  Pairs are laid out
+// in breadth-first order from the root, so that the first K records are the top of the tree: the walker
+// CTAs of the offload mode stage exactly that prefix in shared memory with one bulk copy
+// (wavefront_walk.cuh), and the upper levels share cache lines for everybody else.  Record indices are
+// private to this layout; topology, child order and therefore visit order are the reference's.
+// *depth (optional) receives the number of levels of interior nodes.
+uint32_t build_pairs(const tb200_bvh_node* nodes, int numNodes, std::vector<BvhPair>* out, int* depth = nullptr)
 {
     out->clear();
+    if (depth) *depth = 0;
     if (numNodes <= 0) return TB_LEAF;   // never traversed: callers skip empty trees
+    if (nodes[0].right_leaf >> 31) return TB_LEAF | nodes[0].left;
     std::vector<uint32_t> pairIndex(numNodes, 0xffffffffu);
-    uint32_t count = 0;
-    for (int i = 0; i < numNodes; ++i)
-        if (!(nodes[i].right_leaf >> 31)) pairIndex[i] = count++;
-    out->resize(count);
+    std::vector<uint32_t> order;   // interior nodes in breadth-first order
+    order.reserve(numNodes / 2 + 1);
+    pairIndex[0] = 0;
+    order.push_back(0);
+    size_t levelEnd = 1;
+    int levels = 1;
+    for (size_t k = 0; k < order.size(); ++k) {
+        if (k == levelEnd) {
+            levelEnd = order.size();
+            levels += 1;
+        }
+        const tb200_bvh_node& n = nodes[order[k]];
+        const uint32_t kids[2] = {n.left, n.right_leaf & 0x7fffffffu};
+        for (uint32_t c : kids) {
+            if ((nodes[c].right_leaf >> 31) || pairIndex[c] != 0xffffffffu) continue;   // leaf, or already placed (malformed input)
+            pairIndex[c] = (uint32_t)order.size();
+            order.push_back(c);
+        }
+    }
+    if (depth) *depth = levels;
+    out->resize(order.size());
     auto ref_of = [&](uint32_t idx) -> uint32_t {
         const tb200_bvh_node& n = nodes[idx];
         return (n.right_leaf >> 31) ? (TB_LEAF | n.left) : pairIndex[idx];
     };
-    for (int i = 0; i < numNodes; ++i) {
-        if (nodes[i].right_leaf >> 31) continue;
-        const uint32_t li = nodes[i].left, ri = nodes[i].right_leaf & 0x7fffffffu;
+    for (size_t k = 0; k < order.size(); ++k) {
+        const tb200_bvh_node& n = nodes[order[k]];
+        const uint32_t li = n.left, ri = n.right_leaf & 0x7fffffffu;
         const tb200_bvh_node& L = nodes[li];
         const tb200_bvh_node& R = nodes[ri];
         BvhPair p;
@@ -137,7 +161,7 @@ uint32_t build_pairs(const tb200_bvh_node* nodes, int numNodes, std::vector<BvhP
         p.left = ref_of(li);
         p.right = ref_of(ri);
         p.pad0 = p.pad1 = 0;
-        (*out)[pairIndex[i]] = p;
+        (*out)[k] = p;
     }
     return ref_of(0);
 }
@@ -317,6 +341,14 @@ struct tb200_renderer {
     std::string workerError;              // a peer's failure message, handed to the calling thread
     bool peerAccess = false;
 
+    // mesh-walk offload (wavefront_walk.cuh): queues in device memory, walker CTAs per launch
+    WalkParams walk;
+    void* dWalkBlock = nullptr;   // one allocation behind every pointer of `walk`
+    size_t walkBlockBytes = 0;
+    int numWalkers = 0;           // 0: the offload mode is off
+    std::vector<int> meshDepth;   // interior levels of every mesh BVH
+    std::vector<int> meshPairs;   // BvhPair records of every mesh
+
     int pipeline = 2;             // 0 = mega (validation), 2 = wavefront (product)
     int hardPhases = 1;           // wavefront scheduling mode (see wavefront2.cuh)
     int wideCta = 0;              // 768-thread CTAs for deep mesh BVHs (see wavefront2.cuh)
@@ -350,6 +382,9 @@ void free_device(tb200_renderer* r)
     r->dCounter = nullptr;
     cudaFree(r->dBandCount);
     r->dBandCount = nullptr;
+    cudaFree(r->dWalkBlock);
+    r->dWalkBlock = nullptr;
+    r->numWalkers = 0;
     cudaFree(r->dFiltered);
     cudaFree(r->dRgb8);
     cudaFree(r->dDither);
@@ -372,6 +407,82 @@ void free_device(tb200_renderer* r)
     r->dRadiance = r->dRaster = nullptr;
 }
 
+// Mesh-walk offload (wavefront_walk.cuh): decided per scene.  Eligible: free-running scenes whose scene
+// level runs as the flat program (<= 16 primitives) and that hold a mesh of more than 4096 triangles whose
+// BVH is no deeper than the reference's own traversal stack (a deeper tree overflows `int stack[32]`,
+// intersection.h:688, in the reference itself).  TINSEL_B200_OFFLOAD=0 turns it off, =1 offloads every
+// mesh (tests); TINSEL_B200_WALKERS=n sets the number of walker CTAs.
+bool setup_offload(tb200_renderer* r, const tb200_scene* s)
+{
+    DScene& sc = r->scene;
+    sc.deferMask = 0u;
+    r->numWalkers = 0;
+    memset(&r->walk, 0, sizeof(r->walk));
+    r->walk.treeletMesh = -1;
+    const char* env = getenv("TINSEL_B200_OFFLOAD");
+    const bool force = env && atoi(env) == 1;
+    if ((env && atoi(env) == 0) || r->hardPhases || sc.numFlat <= 0 || s->numPrimitives > 16) return true;
+    int bigMesh = -1, bigTris = 0;
+    for (int i = 0; i < s->numPrimitives; ++i) {
+        const tb200_primitive& p = s->primitives[i];
+        if (p.type != TB200_MESH) continue;
+        const int tris = s->meshes[p.mesh].numIndices / 3;
+        if ((tris > 4096 || force) && r->meshDepth[p.mesh] <= TB_STACK) {
+            sc.deferMask |= 1u << i;
+            if (tris > bigTris) {
+                bigTris = tris;
+                bigMesh = p.mesh;
+            }
+        }
+    }
+    if (sc.deferMask == 0u) return true;
+
+    // queues: a request ring with more cells than the device has path slots (one request per slot at most),
+    // two answer rings of TB_WF2_PATHS cells per shader CTA, a handful of counters
+    const int ctas = std::max(1, r->numSMs);
+    unsigned int log2 = 10;
+    while ((1ull << log2) < (unsigned long long)ctas * TB_WF2_SLOTS) ++log2;
+    const size_t reqBytes = (size_t(1) << log2) * 48, ansBytes = size_t(ctas) * 2 * TB_WF2_SLOTS * 48;
+    const size_t ctrBytes = (size_t(ctas) * 2 + 16) * sizeof(unsigned int);
+    r->walkBlockBytes = reqBytes + ansBytes + ctrBytes;
+    TB_CUDA(cudaMalloc(&r->dWalkBlock, r->walkBlockBytes));
+    TB_CUDA(cudaMemset(r->dWalkBlock, 0, r->walkBlockBytes));
+    char* base = (char*)r->dWalkBlock;
+    WalkParams& W = r->walk;
+    W.reqRing = (uint4*)base;
+    W.reqLog2 = log2;
+    W.ansRing = (uint4*)(base + reqBytes);
+    unsigned int* ctr = (unsigned int*)(base + reqBytes + ansBytes);
+    W.reqTail = ctr + 0;
+    W.reqHead = ctr + 1;
+    W.shadersDone = ctr + 2;
+    W.walkersDone = ctr + 3;
+    W.abortFlag = ctr + 4;
+    W.ansTail = ctr + 16;
+    W.treeletMesh = bigMesh;
+    W.treeletPairs = bigMesh >= 0 ? r->meshPairs[bigMesh] : 0;
+    const char* nw = getenv("TINSEL_B200_WALKERS");
+    r->numWalkers = nw ? atoi(nw) : (ctas * 3) / 8;
+    r->numWalkers = std::max(1, std::min(r->numWalkers, ctas - 1));
+    r->tunePhase = 3;   // the split-queue tuner belongs to the inline walk
+    return true;
+}
+
+// After a launch of the offload mode has been waited for: did a watchdog fire?  (It never should: the
+// flag means shader and walker CTAs stopped waiting for each other after seconds without progress.)
+bool check_offload(tb200_renderer* r)
+{
+    if (r->numWalkers <= 0 || !r->dWalkBlock) return true;
+    unsigned int flag = 0;
+    TB_CUDA(cudaMemcpyAsync(&flag, r->walk.abortFlag, sizeof(flag), cudaMemcpyDeviceToHost, r->stream));
+    TB_CUDA(cudaStreamSynchronize(r->stream));
+    if (flag == 0u) return true;
+    cudaMemsetAsync(r->dWalkBlock, 0, r->walkBlockBytes, r->stream);   // queues and counters back to a clean state
+    cudaStreamSynchronize(r->stream);
+    return set_error(flag == 1u ? "mesh-walk offload: a shader CTA waited for the walkers without progress (watchdog); the frame is incomplete"
+                                : "mesh-walk offload: a walker CTA waited for requests without progress (watchdog); the frame is incomplete");
+}
+
 bool build_scene(tb200_renderer* r, const tb200_scene* s)
 {
     uint64_t* h2d = &r->stats.h2dBytes;
@@ -379,10 +490,15 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
 
     // meshes: pairs + pre-gathered triangles
     std::vector<DMesh> meshes(s->numMeshes);
+    r->meshDepth.clear();
+    r->meshPairs.clear();
     for (int m = 0; m < s->numMeshes; ++m) {
         const tb200_mesh& g = s->meshes[m];
         std::vector<BvhPair> pairs;
-        const uint32_t root = build_pairs(g.nodes, g.numNodes, &pairs);
+        int depth = 0;
+        const uint32_t root = build_pairs(g.nodes, g.numNodes, &pairs, &depth);
+        r->meshDepth.push_back(depth);
+        r->meshPairs.push_back((int)pairs.size());
         const int numTris = g.numIndices / 3;
         std::vector<float4> verts(size_t(numTris) * 3), norms(size_t(numTris) * 3);
         for (int t = 0; t < numTris; ++t) {
@@ -512,6 +628,7 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
     if (!upload(flat, &r->dFlat, h2d)) return false;
     sc.flat = r->dFlat;
     sc.numFlat = (int)flat.size();
+    if (!setup_offload(r, s)) return false;
     sc.rootRef = sceneRoot;
     sc.meshes = r->dMeshes;
     sc.numMeshes = s->numMeshes;
@@ -598,6 +715,8 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     }
     P->shard = r->shard;
     P->numShards = r->numShards;
+    P->walk = r->walk;
+    P->walk.numWalkers = r->numWalkers;
     finalize_params(P);
     return true;
 }
@@ -653,6 +772,7 @@ void tune_update(tb200_renderer* r)
 bool finish_timing(tb200_renderer* r)
 {
     TB_CUDA(cudaStreamSynchronize(r->stream));
+    if (!check_offload(r)) return false;
     float ms = 0.0f;
     TB_CUDA(cudaEventElapsedTime(&ms, r->evStart, r->evStop));
     r->stats.gpuMs = ms;
@@ -686,7 +806,7 @@ bool read_back(tb200_renderer* r, float* output)
         TB_CUDA(cudaMemcpyAsync((char*)output + size_t(row0) * rowBytes, accum + size_t(row0) * rowBytes, bytes, cudaMemcpyDeviceToHost, r->stream));
     TB_CUDA(cudaStreamSynchronize(r->stream));
     r->stats.d2hBytes += bytes;
-    return true;
+    return check_offload(r);
 }
 
 // One frame of the wavefront kernel with the read-back streamed underneath it: samples are handed
@@ -747,7 +867,7 @@ bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output, bool rec
     TB_CUDA(cudaStreamSynchronize(r->copyStream));
     if (copyFailed) TB_CUDA(cudaErrorUnknown);
     r->stats.d2hBytes += size_t(own1 - own0) * rowBytes;
-    return true;
+    return check_offload(r);
 }
 
 }  // namespace
@@ -978,7 +1098,7 @@ tb200_renderer* tb200_create_multi(const tb200_scene* scene, const int* devices,
     }
     for (int a = 0; a < numDevices; ++a)
         for (int b = 0; b < a; ++b)
-            if (devices[a] == devices[b]) {
+            if (devices[a] == devices[b] && !getenv("TINSEL_B200_TEST_DUP_DEVICES")) {   // test hook: a one-GPU box
                 set_error("tb200_create_multi: a device is listed twice");
                 return nullptr;
             }
@@ -1007,7 +1127,7 @@ tb200_renderer* tb200_create_multi(const tb200_scene* scene, const int* devices,
         head->peers.push_back(p);
         // device-to-device gathers go over NVLink when the pair allows peer access
         int can = 0;
-        if (cudaDeviceCanAccessPeer(&can, p->device, head->device) == cudaSuccess && can) {
+        if (p->device != head->device && cudaDeviceCanAccessPeer(&can, p->device, head->device) == cudaSuccess && can) {
             cudaSetDevice(p->device);
             if (cudaDeviceEnablePeerAccess(head->device, 0) != cudaSuccess) cudaGetLastError();
         }
@@ -1307,6 +1427,24 @@ int tb200_gather_device(tb200_renderer* r)
 
 int tb200_num_devices(const tb200_renderer* r) { return r ? (int)r->peers.size() + 1 : 0; }
 
+void tb200_slab_rows(int height, int member, int numMembers, int* firstRow, int* numRows)
+{
+    if (numMembers < 1) numMembers = 1;
+    member = std::max(0, std::min(member, numMembers - 1));
+    const int a = slab_cut(std::max(0, height), member, numMembers), b = slab_cut(std::max(0, height), member + 1, numMembers);
+    if (firstRow) *firstRow = a;
+    if (numRows) *numRows = b - a;
+}
+
+void tb200_slab_traced_rows(int height, int firstRow, int numRows, float filterWidth, int* firstTraced, int* numTraced)
+{
+    const int reach = filter_reach(filterWidth);
+    const int lo = std::max(0, std::min(firstRow, height)), hi = std::max(lo, std::min(firstRow + std::max(0, numRows), height));
+    const int t0 = std::max(0, lo - reach);
+    if (firstTraced) *firstTraced = t0;
+    if (numTraced) *numTraced = hi > lo ? std::min(height, hi + reach) - t0 : 0;
+}
+
 static int render_n_one(tb200_renderer* r, const tb200_camera* camera, const tb200_options* options, int n, float* output)
 {
     cudaSetDevice(r->device);
@@ -1530,6 +1668,7 @@ int tb200_trace_frame(tb200_renderer* r, const tb200_camera* camera, const tb200
         return -1;
     }
     r->stats.d2hBytes += n * 5 * sizeof(float);
+    if (!check_offload(r)) return -1;
     return 0;
 }
 

@@ -3,6 +3,24 @@
 
 #include "tb_film.cuh"
 
+// Mesh-walk offload of the wavefront kernel (wavefront_walk.cuh): the queues between shader CTAs and
+// walker CTAs, in global memory.  numWalkers == 0: the launch does not use it.
+#define TB_WF2_SLOTS 1024   // path slots per CTA of the wavefront kernel (= TB_WF2_PATHS, wavefront2.cuh)
+struct WalkParams {
+    uint4* reqRing;                // (1 << reqLog2) cells x 3 chunks of 16 bytes
+    unsigned int reqLog2;
+    unsigned int* reqTail;
+    unsigned int* reqHead;
+    uint4* ansRing;                // [shader CTA][2][1024] cells x 3 chunks
+    unsigned int* ansTail;         // [shader CTA][2]
+    unsigned int* shadersDone;     // shader CTAs that have exited (this launch)
+    unsigned int* walkersDone;
+    unsigned int* abortFlag;       // set by a watchdog: everybody leaves, the host reports an error
+    int numShaders, numWalkers;
+    int treeletMesh;               // the mesh whose top-of-tree the walkers stage in shared memory (pairs in BFS order)
+    int treeletPairs;              // its number of pairs
+};
+
 struct LaunchParams {
     DScene scene;
     DCamera camera;
@@ -30,6 +48,7 @@ struct LaunchParams {
     volatile unsigned int* bandFlags; // device pointer to pinned, mapped host memory
     unsigned int bandSamples;
     unsigned int bandTag;
+    WalkParams walk;
 };
 
 #define TB_MAX_BANDS 64

@@ -101,6 +101,9 @@ struct DScene {
     // the mesh or none does.
     int splitValid;
     V3 splitLo, splitHi;
+    // Offload mode of the wavefront kernel (wavefront_walk.cuh): bit i set = primitive i is a big mesh
+    // whose BVH walk runs on the walker CTAs; trace_partial() skips it and reports the rays that reach it.
+    uint32_t deferMask;
 };
 
 struct Hit {
@@ -444,6 +447,92 @@ TB_DEV Hit trace_closest(const DScene& sc, V3 o, V3 d, float time, bool wantNorm
         }
     }
     if (tie) return trace_ordered(sc, o, d, time, wantNormal);
+    Hit h;
+    h.t = minT;
+    h.prim = closest;
+    V3 nrm = v3s(0.0f);
+    if (wantNormal && closest >= 0) {
+        rec[ri].t = minT;
+        nrm = prim_normal(sc, sc.prims[closest], o, d, time, rec[ri]);
+    }
+    h.n = face_forward(nrm, -d);
+    return h;
+}
+
+
+// trace_closest() for the offload mode of the wavefront kernel: the primitives of sc.deferMask (big
+// meshes) are not intersected here -- a ray that reaches one (its box test passed, or it sits behind
+// infinite boxes) gets that primitive's bit in `pending` and the caller posts it to the walker CTAs.
+// The hit returned covers all other primitives; merging it with the walkers' answer gives exactly
+// trace_closest()'s result, because the closest hit over a set of primitives does not depend on the
+// order they are tested in, EXCEPT for exact ties in t -- which the scene program detects among its
+// own primitives (below), the walkers among theirs, and the merge between the two; every tie is redone
+// with the reference-order walk.  Falls back to the complete trace_ordered() (pending == 0) for the
+// same rays trace_closest() does.
+TB_DEV Hit trace_partial(const DScene& sc, V3 o, V3 d, float time, bool wantNormal, uint32_t& pending)
+{
+    pending = 0u;
+    const int n = sc.numFlat;
+    const bool guard = (fabsf(o.x) < 1.0e7f) & (fabsf(o.y) < 1.0e7f) & (fabsf(o.z) < 1.0e7f) & (d.x == d.x) & (d.y == d.y) &
+                       (d.z == d.z);
+    if (n == 0 || !guard) return trace_ordered(sc, o, d, time, wantNormal);
+
+    V3 rcp;
+    rcp.x = 1.0f / d.x;
+    rcp.y = 1.0f / d.y;
+    rcp.z = 1.0f / d.z;
+
+    float minT = FLT_MAX;
+    int closest = -1;
+    bool tie = false;
+    PrimHit rec[2];
+    int ri = 0;
+    rec[0].t = 0.0f; rec[0].tri = 0; rec[0].u = rec[0].v = rec[0].w = 0.0f; rec[0].gn = v3s(0.0f);
+    uint32_t visited = 0u;
+    uint32_t wait = 0u;
+
+    for (int i = 0; i < n; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(sc.flat[i].a);
+        const float4 bk = *reinterpret_cast<const float4*>(sc.flat[i].b);   // b[0], b[1], kindPrim, bits
+        const int kindPrim = __float_as_int(bk.z), bits = __float_as_int(bk.w);
+        const int gbit = bits & 0xff;
+        if (gbit != TB_BIT_ALWAYS && !((visited >> gbit) & 1u)) continue;
+        const int kind = kindPrim & 0xff;
+        float t;
+        if (kind == TB_OP_PLANE) {
+            const float dd = a.x * d.x + a.y * d.y + a.z * d.z + a.w * 0.0f;
+            if (dd == 0.0f) continue;
+            t = -(a.x * o.x + a.y * o.y + a.z * o.z + a.w * 1.0f) / dd;
+        } else {
+            if (kind != TB_OP_LEAF) {
+                float tbox;
+                if (!ray_aabb(o, rcp, a.x, a.y, a.z, a.w, bk.x, bk.y, tbox)) continue;
+                if (kind == TB_OP_BOX) {
+                    visited |= 1u << ((bits >> 8) & 0xff);
+                    continue;
+                }
+            }
+            const int prim = kindPrim >> 8;
+            if ((sc.deferMask >> prim) & 1u) {
+                wait |= 1u << prim;
+                continue;
+            }
+            PrimHit* ph = &rec[ri ^ 1];
+            if (!prim_test(sc, sc.prims[prim], o, d, time, *ph)) continue;
+            t = ph->t;
+            if (t > 0.0f && t < minT) ri ^= 1;
+        }
+        if (t > 0.0f) {
+            if (t < minT) {
+                minT = t;
+                closest = kindPrim >> 8;
+            } else if (t == minT) {
+                tie = true;
+            }
+        }
+    }
+    if (tie) return trace_ordered(sc, o, d, time, wantNormal);
+    pending = wait;
     Hit h;
     h.t = minT;
     h.prim = closest;

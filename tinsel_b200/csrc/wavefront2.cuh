@@ -33,6 +33,7 @@
 // second trace queue for rays that enter a big mesh.
 #pragma once
 
+#include <algorithm>
 #include <mutex>
 
 #ifndef TB_WF2_THREADS
@@ -47,6 +48,7 @@
 #ifndef TB_WF2_CTAS_PER_SM
 #define TB_WF2_CTAS_PER_SM 1
 #endif
+static_assert(TB_WF2_PATHS == TB_WF2_SLOTS, "the host sizes the offload queues with TB_WF2_SLOTS");
 #define TB_WF2_MAX_PRIMS 16     // scene tables up to this size are staged in shared memory
 #define TB_WF2_MAX_PAIRS 16
 
@@ -87,6 +89,11 @@ struct Wf2Shared {
     int pref;                         // stage the warps currently prefer (soft phases, see the main loop)
     int live;                         // slots that still hold (or may still receive) a path
     int exhausted;
+    // offload mode: heads of this CTA's two answer rings (extension / shadow), answers still owed to it,
+    // and whether the CTA has told the walkers that it is done
+    unsigned int ansHead[2];
+    int ansPending[2];
+    int exitSignaled;
     // scene tables staged on chip
     DPrim prims[TB_WF2_MAX_PRIMS];
     BvhPair pairs[TB_WF2_MAX_PAIRS];
@@ -315,6 +322,93 @@ TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf
     return true;
 }
 
+#include "wavefront_walk.cuh"
+
+// Claim up to 32 answers of the walkers for this CTA (offload mode): lane i < n receives the three
+// chunks of its answer.  Cells are validated by their lap tags, ownership is taken with a CAS on the
+// ring's head in shared memory (only this CTA's warps consume the ring).
+TB_DEV int wf2_claim_answers(Wf2Shared& S, const WalkParams& W, int kind, int minCount, uint4& c0, uint4& c1, uint4& c2)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned int h = 0;
+    int owed = 0;
+    if (lane == 0) {
+        owed = *(volatile int*)&S.ansPending[kind];
+        h = *(volatile unsigned int*)&S.ansHead[kind];
+    }
+    owed = __shfl_sync(0xffffffffu, owed, 0);
+    if (owed < minCount) return 0;   // nothing (or not enough) can have arrived: skip the round trip to L2
+    h = __shfl_sync(0xffffffffu, h, 0);
+    const unsigned int idx = h + (unsigned)lane;
+    const unsigned int tag = (idx >> WF2_LOG2_PATHS) + 1u;
+    const uint4* cell = W.ansRing + ((size_t)(blockIdx.x * 2 + kind) * TB_WF2_PATHS + (idx & WF2_MASK)) * 3;
+    c0 = walk_ld(cell + 0);
+    c1 = walk_ld(cell + 1);
+    c2 = walk_ld(cell + 2);
+    const bool ok = c0.w == tag && c1.w == tag && c2.w == tag;
+    const unsigned good = __ballot_sync(0xffffffffu, ok);
+    const int n = (good == 0xffffffffu) ? 32 : __ffs(~good) - 1;
+    if (n <= 0 || n < minCount) return 0;
+    unsigned int got = 0;
+    if (lane == 0) got = atomicCAS(&S.ansHead[kind], h, h + (unsigned)n);
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (got != h) return 0;   // another warp of the CTA took them
+    if (lane == 0) atomicSub(&S.ansPending[kind], n);
+    return n;
+}
+
+// Fold a walker's answer into the partial hit stage T left in the slot (offload mode).  Afterwards
+// the slot holds exactly what trace_closest() would have produced for the pending ray.
+TB_DEV void wf2_merge_answer(Wf2Shared& S, const DScene& sc, int s, bool isExt, uint4 c0, uint4 c1, uint4 c2)
+{
+    const uint32_t info = c2.z;
+    const bool hit = ((info >> 18) & 1u) != 0u, tie = ((info >> 19) & 1u) != 0u;
+    const int primM = (int)((info >> 10) & 0xffu);
+    const float tM = __uint_as_float(c0.x);
+    const float partialT = isExt ? S.ht[s] : S.st[s];
+    const int partialPrim = isExt ? S.hprim[s] : S.sprim[s];
+    V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
+    V3 d = v3(S.dx[s], S.dy[s], S.dz[s]);
+    const float time = S.time[s];
+    if (!isExt) {
+        // the shadow ray, as stage T built it (render.cpp:121,170)
+        const V3 p = o + d * S.ht[s];
+        const V3 nn = v3(S.hnx[s], S.hny[s], S.hnz[s]);
+        d = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
+        o = p + face_forward(nn, d) * TB_RAY_EPS;
+    }
+    if (tie || (hit && partialPrim >= 0 && tM == partialT)) {
+        // two primitives at exactly the same t: the reference's visit order decides -- redo in that order
+        const Hit h = trace_ordered(sc, o, d, time, isExt);
+        if (isExt) {
+            S.ht[s] = h.t;
+            S.hnx[s] = h.n.x; S.hny[s] = h.n.y; S.hnz[s] = h.n.z;
+            S.hprim[s] = h.prim;
+        } else {
+            S.st[s] = h.t;
+            S.sprim[s] = h.prim;
+        }
+        return;
+    }
+    if (!hit || !(tM < partialT)) return;   // the partial hit stands
+    if (isExt) {
+        PrimHit ph;
+        ph.t = tM;
+        ph.u = __uint_as_float(c0.y);
+        ph.v = __uint_as_float(c0.z);
+        ph.w = __uint_as_float(c1.x);
+        ph.gn = v3(__uint_as_float(c1.y), __uint_as_float(c1.z), __uint_as_float(c2.x));
+        ph.tri = (int)c2.y;
+        const V3 n = face_forward(prim_normal(sc, sc.prims[primM], o, d, time, ph), -d);
+        S.ht[s] = tM;
+        S.hnx[s] = n.x; S.hny[s] = n.y; S.hnz[s] = n.z;
+        S.hprim[s] = primM;
+    } else {
+        S.st[s] = tM;
+        S.sprim[s] = primM;
+    }
+}
+
 // THREADS: 512 (16 warps, up to 128 registers) for scenes held in shared memory, where more warps
 // only add instruction-cache pressure; 768 (24 warps, 80 registers) for scenes with deep mesh BVHs,
 // whose traversal is latency bound on L2 and pays for the extra warps (LaunchParams::wideCta).
@@ -325,7 +419,8 @@ TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf
 //                     its own specialisation measured 5 % slower on cornell)
 //   WF2_MODE_HARD     hard phases only (veach +4 %)
 //   WF2_MODE_SPLIT    free-running with the split trace queue TM (scenes with a big mesh)
-enum { WF2_MODE_GENERIC = 0, WF2_MODE_HARD = 1, WF2_MODE_SPLIT = 2 };
+//   WF2_MODE_OFFLOAD  free-running shader CTAs + walker CTAs that do the big meshes' BVH walks (wavefront_walk.cuh)
+enum { WF2_MODE_GENERIC = 0, WF2_MODE_HARD = 1, WF2_MODE_SPLIT = 2, WF2_MODE_OFFLOAD = 3 };
 
 template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(LaunchParams P, unsigned long long total)
@@ -333,6 +428,11 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     extern __shared__ __align__(16) unsigned char wf_smem_raw[];
     Wf2Shared& S = *reinterpret_cast<Wf2Shared*>(wf_smem_raw);
     const int tid = threadIdx.x;
+    constexpr bool offload = MODE == WF2_MODE_OFFLOAD;
+    if (offload && (int)blockIdx.x >= P.walk.numShaders) {
+        wf2_walker_role<THREADS>(P, wf_smem_raw, (int)sizeof(Wf2Shared));
+        return;
+    }
 
     // ---- prologue: stage the scene tables on chip ---------------------------------------------
     DScene sc = P.scene;
@@ -377,6 +477,13 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
         S.pref = WF2_Q_R;
         S.live = TB_WF2_PATHS;
         S.exhausted = 0;
+        S.ansPending[0] = S.ansPending[1] = 0;
+        S.exitSignaled = 0;
+        if (offload) {
+            // everything the walkers ever answered has been consumed: the rings' heads are their tails
+            S.ansHead[0] = walk_ld1(P.walk.ansTail + blockIdx.x * 2 + 0);
+            S.ansHead[1] = walk_ld1(P.walk.ansTail + blockIdx.x * 2 + 1);
+        }
     }
     __syncthreads();
 
@@ -394,7 +501,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     //    CTA-wide preferred stage and moving on cyclically when that queue has no full chunk left
     //    (dragging the preference along).  Nobody ever waits for a slow ray, which wins when ray
     //    cost varies wildly (deep mesh BVHs) and the hot loop is small enough to stay cached.
-    const bool hard = MODE == WF2_MODE_HARD ? true : MODE == WF2_MODE_SPLIT ? false : (P.hardPhases != 0);
+    const bool hard = MODE == WF2_MODE_HARD ? true : (MODE == WF2_MODE_SPLIT || offload) ? false : (P.hardPhases != 0);
     constexpr bool split = MODE == WF2_MODE_SPLIT;
     // hard-phase schedule: each cycle is two block-synchronous phases,
     //   phase 0:  R (finished slots -> fresh camera rays into F[cycle&1]),  T,  F[~cycle&1]
@@ -406,8 +513,11 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     unsigned int stepTail = TB_WF2_PATHS;   // every slot starts in the R queue
     int stepQueue = WF2_Q_R;
 
+    unsigned int idleSpins = 0;
     for (;;) {
         int s = 0, n = 0, stage = -1;
+        bool fromAnswer = false;      // offload mode: the chunk are walkers' answers, merged at the head of stage A / B
+        uint4 ans0 = make_uint4(0u, 0u, 0u, 0u), ans1 = ans0, ans2 = ans0;
         if (hard) {
             n = wf2_claim_ticket(S, stepQueue, stepTail, s);
             if (n > 0) {
@@ -451,7 +561,26 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             int p = 0;
             if (lane == 0) p = *(volatile int*)&S.pref;
             p = __shfl_sync(0xffffffffu, p, 0);
-            if (!split) {
+            if (offload) {
+                // sweep over six sources: T, answers(ext), A, answers(shadow), B, R
+                for (int k = 0; k < 12 && stage < 0; ++k) {
+                    const int pos = (p + k) % 6;
+                    const int minCount = k < 6 ? 32 : 1;
+                    if (pos == 1 || pos == 3) {
+                        n = wf2_claim_answers(S, P.walk, pos == 1 ? WALK_KIND_EXT : WALK_KIND_SHADOW, minCount, ans0, ans1, ans2);
+                        if (n > 0) {
+                            stage = pos == 1 ? WF2_Q_A : WF2_Q_B;
+                            fromAnswer = true;
+                            s = (int)(ans2.z & 1023u);
+                        }
+                    } else {
+                        const int q = pos == 0 ? WF2_Q_T : pos == 2 ? WF2_Q_A : pos == 4 ? WF2_Q_B : WF2_Q_R;
+                        n = wf2_claim(S, q, minCount, s);
+                        if (n > 0) stage = q;
+                    }
+                    if (n > 0 && pos != p && lane == 0) *(volatile int*)&S.pref = pos;
+                }
+            } else if (!split) {
                 for (int k = 0; k < 8 && stage < 0; ++k) {
                     // k = 0..3: full chunks only; k = 4..7: whatever is left
                     const int q = (p + k) & 3;
@@ -470,12 +599,25 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                     }
                 }
             }
-            if (!split && stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
+            if (!split && !offload && stage >= 0 && stage != p && lane == 0) *(volatile int*)&S.pref = stage;
             if (stage < 0) {
                 if (*(volatile int*)&S.live <= 0) break;
+                if (offload) {
+                    // parked slots wait for the walkers: a watchdog instead of an endless spin if they never answer
+                    if ((++idleSpins & 255u) == 0u) {
+                        unsigned int bad = 0;
+                        if (lane == 0) bad = walk_ld1(P.walk.abortFlag);
+                        if (__shfl_sync(0xffffffffu, bad, 0)) break;
+                        if (idleSpins > WALK_WATCHDOG_SPINS) {
+                            if (lane == 0) atomicExch(P.walk.abortFlag, 1u);
+                            break;
+                        }
+                    }
+                }
                 __nanosleep(200);
                 continue;
             }
+            idleSpins = 0;
         }
         const bool active = lane < n;
 
@@ -548,6 +690,9 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
         } else if (stage == WF2_Q_T || stage >= WF2_Q_F0) {
             // ===================== T: trace the pending ray =======================================
             bool isExt = false, isNee = false;
+            uint32_t parkMask = 0u;       // offload mode: big meshes the ray still has to be walked through
+            V3 postO = v3s(0.0f), postD = v3s(0.0f);
+            float postTime = 0.0f;
             if (active) {
                 const uint32_t fl = S.flags[s];
                 V3 o = v3(S.ox[s], S.oy[s], S.oz[s]);
@@ -564,7 +709,12 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                 }
                 if (isNee || maxDepth > 0) {
                     // one traversal instance serves both ray kinds (normals only for extension rays)
-                    const Hit h = trace_closest(sc, o, d, time, isExt);
+                    const Hit h = offload ? trace_partial(sc, o, d, time, isExt, parkMask) : trace_closest(sc, o, d, time, isExt);
+                    if (offload) {
+                        postO = o;
+                        postD = d;
+                        postTime = time;
+                    }
                     if (isExt) {
                         S.ht[s] = h.t;
                         S.hnx[s] = h.n.x; S.hny[s] = h.n.y; S.hnz[s] = h.n.z;
@@ -578,11 +728,25 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                 }
             }
             __threadfence_block();
+            if (offload) {
+                // rays that reach a big mesh park in their slot; the walkers' answer re-enters at stage A / B
+                const bool park = parkMask != 0u;
+                const unsigned pe = __ballot_sync(0xffffffffu, park && isExt), pn = __ballot_sync(0xffffffffu, park && isNee);
+                if (lane == 0) {
+                    if (pe) atomicAdd(&S.ansPending[WALK_KIND_EXT], __popc(pe));
+                    if (pn) atomicAdd(&S.ansPending[WALK_KIND_SHADOW], __popc(pn));
+                }
+                walk_post(P.walk, park, postO, postD, postTime, parkMask,
+                          (uint32_t)s | ((isExt ? WALK_KIND_EXT : WALK_KIND_SHADOW) << 10) | ((uint32_t)blockIdx.x << 11));
+                isExt = isExt && !park;
+                isNee = isNee && !park;
+            }
             wf2_push(S, WF2_Q_A, isExt, s);
             wf2_push(S, WF2_Q_B, isNee, s);
         } else if (stage == WF2_Q_A) {
             // ===================== A: extension-ray results =======================================
             bool cont = false, fin = false;
+            if (offload && fromAnswer && active) wf2_merge_answer(S, sc, s, true, ans0, ans1, ans2);
             if (active) {
                 const uint32_t fl = S.flags[s];
                 const int bounce = (int)(fl >> 8);
@@ -643,6 +807,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
         } else {
             // ===================== B: shadow-ray results ==========================================
             bool cont = false, fin = false;
+            if (offload && fromAnswer && active) wf2_merge_answer(S, sc, s, false, ans0, ans1, ans2);
             if (active) {
                 const uint32_t fl = S.flags[s];
                 const int bounce = (int)(fl >> 8);
@@ -687,6 +852,13 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             wf2_push(S, WF2_Q_R, fin, s);
         }
     }
+    if (offload) {
+        // this CTA posts no more requests: tell the walkers (once)
+        if (lane == 0 && atomicExch(&S.exitSignaled, 1) == 0) {
+            __threadfence();
+            atomicAdd(P.walk.shadersDone, 1u);
+        }
+    }
 }
 
 // The opt-in to > 48 KB of dynamic shared memory and the occupancy answer are PER DEVICE (and the
@@ -718,6 +890,17 @@ static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t 
     // TB_WF2_CTAS_PER_SM resident CTAs per SM; small jobs use fewer so that every CTA has a full slot array
     const unsigned long long want = (total + TB_WF2_PATHS - 1) / TB_WF2_PATHS;
     int grid = (numSMs > 0 ? numSMs : 148) * ctasPerSM;
+    if (MODE == WF2_MODE_OFFLOAD) {
+        // shader CTAs [0, numShaders) + walker CTAs behind them, all resident at once (they wait for each other)
+        LaunchParams q = p;
+        int walkers = std::max(1, std::min(q.walk.numWalkers, grid - 1));
+        int shaders = grid - walkers;
+        if (want < (unsigned long long)shaders) shaders = (int)std::max<unsigned long long>(1ull, want);
+        q.walk.numShaders = shaders;
+        q.walk.numWalkers = walkers;
+        k_wavefront2<THREADS, MODE><<<shaders + walkers, THREADS, sizeof(Wf2Shared), stream>>>(q, total);
+        return;
+    }
     if (want < (unsigned long long)grid) grid = (int)want;
     if (grid < 1) grid = 1;
     k_wavefront2<THREADS, MODE><<<grid, THREADS, sizeof(Wf2Shared), stream>>>(p, total);
@@ -729,6 +912,12 @@ void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, u
     if (total == 0ull) return;
     cudaMemsetAsync(p.sampleCounter, 0, sizeof(unsigned long long), stream);
     const bool split = !p.hardPhases && p.scene.splitValid;
+    if (p.walk.numWalkers > 0 && !p.hardPhases && p.scene.deferMask != 0u && p.scene.numFlat > 0) {
+        if (p.wideCta) launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_OFFLOAD>(p, numSMs, stream, total);
+        else launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_OFFLOAD>(p, numSMs, stream, total);
+        if (launchCount) ++*launchCount;
+        return;
+    }
     if (p.wideCta) {
         if (split) launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_SPLIT>(p, numSMs, stream, total);
         else launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_GENERIC>(p, numSMs, stream, total);
