@@ -147,40 +147,31 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
     mh.t = FLT_MAX; mh.tri = -1; mh.prim = -1; mh.u = mh.v = mh.w = 0.0f; mh.gn = v3s(0.0f);
     bool tie = false;
     unsigned int idleSpins = 0;
-    int fillWait = 0;             // iterations until the refill action may be chosen again after a fruitless poll
+    int fillWait = 0;             // passes until FILL may run again after a fruitless poll
 
     const unsigned int reqMask = (1u << W.reqLog2) - 1u;
 
-    // Every iteration the WARP performs ONE action, chosen by vote, with all lanes that are ready for it:
-    //   BOX   an interior-node step            TRI   a triangle test
-    //   NEXT  a mesh (or nothing yet) is finished: fold its hit, set up the request's next mesh, or answer
-    //   FILL  idle lanes take tickets (one atomic for the warp), ticket holders poll their request cell
-    // Lanes that are ready for something else wait a turn: the price of never executing two branches per
-    // iteration, which is what a ray-per-lane loop with data-dependent branches would do.
-    for (;;) {
-        const bool wBox = phase == PH_WALK && cur != EMPTY && (cur & TB_LEAF) == 0u;
-        const bool wTri = phase == PH_WALK && cur != EMPTY && (cur & TB_LEAF) != 0u;
-        const bool wNext = phase == PH_WALK && cur == EMPTY;
-        const bool wFill = phase == PH_IDLE || phase == PH_TICKET;
-        const int nBox = __popc(__ballot_sync(0xffffffffu, wBox));
-        const int nTri = __popc(__ballot_sync(0xffffffffu, wTri));
-        const int nNext = __popc(__ballot_sync(0xffffffffu, wNext));
-        const unsigned mFill = __ballot_sync(0xffffffffu, wFill);
-        const int nFill = __popc(mFill);
-        const int busy = nBox + nTri + nNext;
-        if (fillWait > 0) fillWait -= 1;
-        int action;   // 0 box, 1 tri, 2 next, 3 fill
-        if (busy == 0) {
-            action = 3;
-        } else {
-            action = 0;
-            int bestN = nBox >= 16 ? 64 : nBox;
-            if (nTri > bestN) { action = 1; bestN = nTri; }
-            if (nNext > bestN) { action = 2; bestN = nNext; }
-            if (fillWait == 0 && nFill >= 8 && nFill > bestN) action = 3;
-        }
+    uint32_t pend = EMPTY;        // a triangle found but not yet tested (speculative traversal, see below)
 
-        if (action == 0) {
+    // The warp cycles through four phases; in each, the lanes that are ready for it work and the others
+    // wait -- never two divergent branches in one pass, which is what a ray-per-lane loop with
+    // data-dependent branches would execute:
+    //   BOX   interior-node steps, repeated while most lanes have one.  A lane that reaches a triangle
+    //         parks it in `pend` and keeps descending (speculatively: its later box tests use a stale,
+    //         larger tmax, so it visits a superset of the reference's nodes; everything in the extra nodes
+    //         lies at t >= the closest hit and fails the strict `t < closestT`, and triangles are still
+    //         tested in the reference's order -- the result is the reference's, bit for bit)
+    //   TRI   the parked triangles are tested
+    //   NEXT  lanes whose mesh is finished fold its hit and set up the request's next mesh, or answer
+    //   FILL  idle lanes take tickets (one atomic for the warp), ticket holders poll their request cell
+    // NEXT and FILL run as soon as a handful of lanes want them: they are what puts lanes back to work.
+    for (;;) {
+        // ---- BOX -----------------------------------------------------------------------------------------
+        int nBox;
+        for (;;) {
+            const bool wBox = phase == PH_WALK && cur != EMPTY && (cur & TB_LEAF) == 0u;
+            nBox = __popc(__ballot_sync(0xffffffffu, wBox));
+            if (nBox == 0) break;
             if (wBox) {
                 // IntersectRayMesh interior step, intersection.h:702-727
                 const BvhPair* pr = (meshId == W.treeletMesh && cur < (uint32_t)treeletPairs) ? treelet + cur : pairs + cur;
@@ -189,111 +180,144 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
                 float tLeft, tRight;
                 const bool hitLeft = ray_aabb(o, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft) && tLeft < tmax;
                 const bool hitRight = ray_aabb(o, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight) && tRight < tmax;
-                uint32_t left = kids.x, right = kids.y;
-                if (hitLeft && hitRight && (tLeft < tRight)) {
-                    const uint32_t tmp = left;
-                    left = right;
-                    right = tmp;
-                }
-                // the reference pushes `left` then `right` and pops `right` first: `right` is next, `left` waits
-                if (hitLeft && hitRight) {
-                    if (sp < TB_STACK) stack[sp * THREADS] = left;   // deeper than the reference's own stack[32]: host refuses such trees
+                // "traverse closest first": the reference pushes the far child, then the near one, and pops the near
+                // one at once (intersection.h:716-727) -- the near child is `nxt`, the far one goes on the stack
+                const bool both = hitLeft && hitRight;
+                const bool swap = both && (tLeft < tRight);
+                const uint32_t far = swap ? kids.y : kids.x;              // what the reference pushes first
+                uint32_t nxt = both ? (swap ? kids.x : kids.y) : (hitLeft ? kids.x : kids.y);
+                if (both) {
+                    if (sp < TB_STACK) stack[sp * THREADS] = far;   // a deeper tree overflows the reference's own stack[32]: the host refuses it
                     sp += 1;
-                    cur = right;
-                } else if (hitLeft) {
-                    cur = left;
-                } else if (hitRight) {
-                    cur = right;
-                } else if (sp > 0) {
-                    sp -= 1;
-                    cur = stack[sp * THREADS];
-                } else {
-                    cur = EMPTY;
                 }
-            }
-        } else if (action == 1) {
-            if (wTri) {
-                // MeshQuery, intersection.h:629-674
-                const uint32_t i = cur & ~TB_LEAF;
-                const float4 q0 = __ldg(&triVerts[i * 3 + 0]);
-                const float4 q1 = __ldg(&triVerts[i * 3 + 1]);
-                const float4 q2 = __ldg(&triVerts[i * 3 + 2]);
-                float t, u, v, w, sign;
-                V3 n;
-                if (ray_tri(o, d, v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), v3(q1.z, q1.w, q2.x), t, u, v, w, sign, n)) {
-                    if (t > 0.0f && t < mh.t) {
-                        mh.t = t;
-                        mh.u = u;
-                        mh.v = v;
-                        mh.w = w;
-                        mh.tri = (int)i;
-                        mh.gn = n * sign;
+                if (!(hitLeft || hitRight)) {
+                    nxt = EMPTY;
+                    if (sp > 0) {
+                        sp -= 1;
+                        nxt = stack[sp * THREADS];
                     }
                 }
-                tmax = mh.t;   // "truncate ray", intersection.h:700
-                if (sp > 0) {
-                    sp -= 1;
-                    cur = stack[sp * THREADS];
-                } else {
-                    cur = EMPTY;
-                }
-            }
-        } else if (action == 2) {
-            if (wNext) {
-                // fold the finished mesh's hit: "t < minT && t > 0", first found wins (render.cpp:45) -- the
-                // reference meets the primitives in BVH order, this loop in index order: only an exact tie in
-                // t can tell the difference, and that is reported
-                if (prim >= 0 && mh.tri >= 0) {
-                    if (mh.t < best.t) {
-                        best = mh;
-                        best.prim = prim;
-                    } else if (mh.t == best.t) {
-                        tie = true;
+                if (nxt != EMPTY && (nxt & TB_LEAF) != 0u && pend == EMPTY) {
+                    // park the triangle, go on with what the reference would pop after testing it
+                    pend = nxt;
+                    nxt = EMPTY;
+                    if (sp > 0) {
+                        sp -= 1;
+                        nxt = stack[sp * THREADS];
                     }
                 }
-                if (maskLeft != 0u) {
-                    V3 ow = o, dw = d;
-                    if (prim >= 0) {
-                        // a second mesh in the same request: the world ray is still in its (unconsumable) ring cell
-                        const uint4 c0 = walk_ld(W.reqRing + (size_t)(ticket & reqMask) * 3 + 0);
-                        const uint4 c1 = walk_ld(W.reqRing + (size_t)(ticket & reqMask) * 3 + 1);
-                        ow = v3(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z));
-                        dw = v3(__uint_as_float(c1.x), __uint_as_float(c1.y), __uint_as_float(c1.z));
+                cur = nxt;
+            }
+            if (nBox < 20) break;   // give the other phases a turn (one step per turn keeps every lane progressing)
+        }
+
+        // ---- TRI -----------------------------------------------------------------------------------------
+        {
+            const int nPend = __popc(__ballot_sync(0xffffffffu, phase == PH_WALK && pend != EMPTY));
+            if (nPend > 0 && (nPend >= 8 || nBox < 16)) {
+                if (phase == PH_WALK && pend != EMPTY) {
+                    // MeshQuery, intersection.h:629-674
+                    const uint32_t i = pend & ~TB_LEAF;
+                    const float4 q0 = __ldg(&triVerts[i * 3 + 0]);
+                    const float4 q1 = __ldg(&triVerts[i * 3 + 1]);
+                    const float4 q2 = __ldg(&triVerts[i * 3 + 2]);
+                    float t, u, v, w, sign;
+                    V3 n;
+                    if (ray_tri(o, d, v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), v3(q1.z, q1.w, q2.x), t, u, v, w, sign, n)) {
+                        if (t > 0.0f && t < mh.t) {
+                            mh.t = t;
+                            mh.u = u;
+                            mh.v = v;
+                            mh.w = w;
+                            mh.tri = (int)i;
+                            mh.gn = n * sign;
+                        }
                     }
-                    prim = __ffs(maskLeft) - 1;
-                    maskLeft &= maskLeft - 1u;
-                    const DPrim& p = sc.prims[prim];
-                    // PrimitiveIntersect, mesh case (intersection.h:982-992): the ray in the mesh's space
-                    const Xf xf = prim_transform(p, rtime);
-                    o = inverse_transform_point(xf, ow);
-                    d = inverse_transform_vector(xf, dw);
-                    rcp.x = 1.0f / d.x;
-                    rcp.y = 1.0f / d.y;
-                    rcp.z = 1.0f / d.z;
-                    meshId = p.mesh;
-                    const DMesh& m = sc.meshes[meshId];
-                    pairs = m.pairs;
-                    triVerts = m.triVerts;
-                    cur = m.rootRef;
-                    sp = 0;
-                    tmax = FLT_MAX;
-                    mh.t = FLT_MAX;
-                    mh.tri = -1;
-                } else {
-                    // the request is finished: answer it
-                    const unsigned int cta = src >> 11, kind = (src >> 10) & 1u, slot = src & 1023u;
-                    const unsigned int idx = atomicAdd(W.ansTail + cta * 2 + kind, 1u);
-                    const unsigned int tag = (idx >> WF2_LOG2_PATHS) + 1u;
-                    uint4* cell = W.ansRing + ((size_t)(cta * 2 + kind) * TB_WF2_PATHS + (idx & WF2_MASK)) * 3;
-                    const uint32_t info = slot | ((uint32_t)(best.prim & 0xff) << 10) | ((best.prim >= 0 ? 1u : 0u) << 18) | ((tie ? 1u : 0u) << 19);
-                    walk_st(cell + 0, __float_as_uint(best.t), __float_as_uint(best.u), __float_as_uint(best.v), tag);
-                    walk_st(cell + 1, __float_as_uint(best.w), __float_as_uint(best.gn.x), __float_as_uint(best.gn.y), tag);
-                    walk_st(cell + 2, __float_as_uint(best.gn.z), (uint32_t)best.tri, info, tag);
-                    phase = PH_IDLE;
+                    tmax = mh.t;   // "truncate ray", intersection.h:700
+                    pend = EMPTY;
+                    if (cur != EMPTY && (cur & TB_LEAF) != 0u) {
+                        // a second triangle was waiting behind the first
+                        pend = cur;
+                        cur = EMPTY;
+                        if (sp > 0) {
+                            sp -= 1;
+                            cur = stack[sp * THREADS];
+                        }
+                    }
                 }
             }
-        } else {
-            // ---- FILL ------------------------------------------------------------------------------------
+        }
+
+        // ---- NEXT ----------------------------------------------------------------------------------------
+        {
+            const bool wNext = phase == PH_WALK && cur == EMPTY && pend == EMPTY;
+            const int nNext = __popc(__ballot_sync(0xffffffffu, wNext));
+            if (nNext > 0 && (nNext >= 4 || nBox < 8)) {
+                if (wNext) {
+                    // fold the finished mesh's hit: "t < minT && t > 0", first found wins (render.cpp:45) -- the
+                    // reference meets the primitives in BVH order, this loop in index order: only an exact tie in
+                    // t can tell the difference, and that is reported
+                    if (prim >= 0 && mh.tri >= 0) {
+                        if (mh.t < best.t) {
+                            best = mh;
+                            best.prim = prim;
+                        } else if (mh.t == best.t) {
+                            tie = true;
+                        }
+                    }
+                    if (maskLeft != 0u) {
+                        V3 ow = o, dw = d;
+                        if (prim >= 0) {
+                            // a second mesh in the same request: the world ray is still in its (unconsumable) ring cell
+                            const uint4 c0 = walk_ld(W.reqRing + (size_t)(ticket & reqMask) * 3 + 0);
+                            const uint4 c1 = walk_ld(W.reqRing + (size_t)(ticket & reqMask) * 3 + 1);
+                            ow = v3(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z));
+                            dw = v3(__uint_as_float(c1.x), __uint_as_float(c1.y), __uint_as_float(c1.z));
+                        }
+                        prim = __ffs(maskLeft) - 1;
+                        maskLeft &= maskLeft - 1u;
+                        const DPrim& p = sc.prims[prim];
+                        // PrimitiveIntersect, mesh case (intersection.h:982-992): the ray in the mesh's space
+                        const Xf xf = prim_transform(p, rtime);
+                        o = inverse_transform_point(xf, ow);
+                        d = inverse_transform_vector(xf, dw);
+                        rcp.x = 1.0f / d.x;
+                        rcp.y = 1.0f / d.y;
+                        rcp.z = 1.0f / d.z;
+                        meshId = p.mesh;
+                        const DMesh& m = sc.meshes[meshId];
+                        pairs = m.pairs;
+                        triVerts = m.triVerts;
+                        cur = m.rootRef;
+                        if ((cur & TB_LEAF) != 0u) {   // a one-triangle mesh: its root is the triangle
+                            pend = cur;
+                            cur = EMPTY;
+                        }
+                        sp = 0;
+                        tmax = FLT_MAX;
+                        mh.t = FLT_MAX;
+                        mh.tri = -1;
+                    } else {
+                        // the request is finished: answer it
+                        const unsigned int cta = src >> 11, kind = (src >> 10) & 1u, slot = src & 1023u;
+                        const unsigned int idx = atomicAdd(W.ansTail + cta * 2 + kind, 1u);
+                        const unsigned int tag = (idx >> WF2_LOG2_PATHS) + 1u;
+                        uint4* cell = W.ansRing + ((size_t)(cta * 2 + kind) * TB_WF2_PATHS + (idx & WF2_MASK)) * 3;
+                        const uint32_t info = slot | ((uint32_t)(best.prim & 0xff) << 10) | ((best.prim >= 0 ? 1u : 0u) << 18) | ((tie ? 1u : 0u) << 19);
+                        walk_st(cell + 0, __float_as_uint(best.t), __float_as_uint(best.u), __float_as_uint(best.v), tag);
+                        walk_st(cell + 1, __float_as_uint(best.w), __float_as_uint(best.gn.x), __float_as_uint(best.gn.y), tag);
+                        walk_st(cell + 2, __float_as_uint(best.gn.z), (uint32_t)best.tri, info, tag);
+                        phase = PH_IDLE;
+                    }
+                }
+            }
+        }
+
+        // ---- FILL ----------------------------------------------------------------------------------------
+        if (fillWait > 0) fillWait -= 1;
+        const int nWalk = __popc(__ballot_sync(0xffffffffu, phase == PH_WALK));
+        const int nFill = __popc(__ballot_sync(0xffffffffu, phase == PH_IDLE || phase == PH_TICKET));
+        if (nFill > 0 && (nWalk == 0 || (fillWait == 0 && (nFill >= 4 || nBox < 8)))) {
             const unsigned idle = __ballot_sync(0xffffffffu, phase == PH_IDLE);
             if (idle != 0u) {
                 const int leader = __ffs(idle) - 1;
@@ -320,6 +344,7 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
                     tie = false;
                     prim = -1;
                     cur = EMPTY;          // NEXT sets up the first mesh of the mask
+                    pend = EMPTY;
                     phase = PH_WALK;
                     got = true;
                 }
@@ -329,7 +354,7 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
                 idleSpins = 0;
             } else {
                 fillWait = 16;
-                if (busy == 0) {
+                if (nWalk == 0) {
                     // nothing to walk in this warp: wait for requests, or leave when the shaders are done.  The
                     // order matters: every ticket below the final tail was filled before the last shader left.
                     unsigned int done = 0, bad = 0;
@@ -351,6 +376,7 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
                             if (!late) phase = PH_RETIRED;
                         }
                         if (!__any_sync(0xffffffffu, late)) break;
+                        fillWait = 0;
                         continue;   // the next FILL picks the late request up
                     }
                     if (++idleSpins > WALK_WATCHDOG_SPINS) {
@@ -360,6 +386,8 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
                     __nanosleep(400);
                 }
             }
+        } else if (nWalk == 0 && nFill == 0) {
+            break;   // every lane of the warp has retired
         }
     }
     // the last walker out squares the request ring for the next launch: tickets taken beyond the final
