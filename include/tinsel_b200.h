@@ -323,6 +323,25 @@ const tb200_mesh* tb200_mesh_bin_mesh(const tb200_mesh_file* f);
 int tb200_mesh_bin_save(const char* path, const tb200_mesh* mesh);  /* 0 on success */
 void tb200_mesh_bin_free(tb200_mesh_file* f);
 
+/* ---- mesh BVH construction on the GPU ---------------------------------------------------------------
+ * Replaces Mesh::RebuildBVH + BVHBuilder::Build (src/mesh.cpp:314-338, src/bvh.h:30-263: one Bounds per
+ * triangle, recursive full-sweep SAH on one host core, 1.33 s for ajax) for triangle meshes: a PLOC
+ * (parallel locally-ordered clustering) build on the device, milliseconds for half a million triangles.
+ * Writes 2*numTriangles-1 nodes in the reference's own BVHNode format (root at 0, one triangle per leaf,
+ * leaf.left = triangle index, node boxes = exact unions of triangle boxes), usable as tb200_mesh::nodes,
+ * by the reference's IntersectRayMesh, and in the .bin mesh cache.  `positions`, `indices`, `outNodes`
+ * are HOST arrays.  The tree differs from the reference builder's (an equally valid input to the same
+ * traversal).  Returns 0 on success; tb200_bvh_build_error() describes a failure. */
+typedef struct tb200_bvh_build_info {
+    int32_t numNodes;          /* 2*numTriangles - 1 */
+    int32_t rounds;            /* clustering rounds */
+    uint64_t kernelLaunches;   /* this library's kernels (the radix sort and prefix sums are CUB calls on top) */
+    double buildMs;            /* device time from the triangle boxes to the finished node array (CUDA events) */
+} tb200_bvh_build_info;
+int tb200_bvh_build(const float* positions, int numVertices, const int32_t* indices, int numIndices,
+                    tb200_bvh_node* outNodes, int device, tb200_bvh_build_info* info);
+const char* tb200_bvh_build_error(void);
+
 #ifdef __cplusplus
 }
 #endif

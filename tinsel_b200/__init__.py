@@ -88,6 +88,10 @@ def load_library():
     lib.tb200_destroy.argtypes = [C.c_void_p]
     lib.tb200_last_error.restype = C.c_char_p
     lib.tb200_last_error.argtypes = []
+    lib.tb200_bvh_build.restype = C.c_int
+    lib.tb200_bvh_build.argtypes = [f32p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_int, C.POINTER(abi.BvhBuildInfo)]
+    lib.tb200_bvh_build_error.restype = C.c_char_p
+    lib.tb200_bvh_build_error.argtypes = []
     abi.declare_snapshot_api(lib)
     _lib = lib
     return lib
@@ -99,6 +103,21 @@ def last_error():
 
 def sample_seed(pixel, frame):
     return load_library().tb200_sample_seed(pixel, frame)
+
+
+def bvh_build(positions, indices, nodes, device=0):
+    """Mesh BVH construction on the GPU (tb200_bvh_build): positions (nv,3) float32, indices (nt,3) int32,
+    nodes: a writable array of 2*nt-1 records of 32 bytes (the reference's BVHNode).  Returns the build info."""
+    lib = load_library()
+    positions = np.ascontiguousarray(positions, np.float32)
+    indices = np.ascontiguousarray(indices, np.int32)
+    assert nodes.nbytes >= (2 * indices.shape[0] - 1) * 32 and nodes.flags["C_CONTIGUOUS"]
+    info = abi.BvhBuildInfo()
+    rc = lib.tb200_bvh_build(_fp(positions), positions.shape[0], indices.ctypes.data_as(C.POINTER(C.c_int32)), indices.size,
+                             nodes.ctypes.data_as(C.c_void_p), device, C.byref(info))
+    if rc != 0:
+        raise TinselB200Error("tb200_bvh_build failed: " + lib.tb200_bvh_build_error().decode())
+    return info
 
 
 def scene_path(name):

@@ -140,6 +140,10 @@ class Stats(C.Structure):
     ]
 
 
+class BvhBuildInfo(C.Structure):
+    _fields_ = [("numNodes", C.c_int32), ("rounds", C.c_int32), ("kernelLaunches", C.c_uint64), ("buildMs", C.c_double)]
+
+
 def copy_struct(s):
     """Value copy of a ctypes structure."""
     out = type(s)()
@@ -150,6 +154,8 @@ def copy_struct(s):
 # Every symbol include/tinsel_b200.h declares (tests/test_abi.py checks the library exports them all).
 EXPORTS = [
     "tb200_create",
+    "tb200_bvh_build",
+    "tb200_bvh_build_error",
     "tb200_create_multi",
     "tb200_num_devices",
     "tb200_slab_rows",

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libtinsel_b200.so")
 
-SOURCES = ["kernels.cu", "api.cu", "snapshot.cpp"]
+SOURCES = ["kernels.cu", "api.cu", "snapshot.cpp", "bvh_build.cu"]
 HEADERS = ["tb_math.cuh", "tb_scene.cuh", "tb_shade.cuh", "tb_film.cuh", "tb_kernels.cuh", "wavefront2.cuh", "wavefront_walk.cuh"]
 
 NVCC_FLAGS = [

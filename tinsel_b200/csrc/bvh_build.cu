@@ -25,6 +25,8 @@
 // order changes, so only exact ties in t between two triangles can be resolved differently from the
 // reference's tree; the criterion (tests/test_bvh_build.py) is therefore: hand the GPU-built tree to
 // the oracle as the mesh's BVH and compare per sample, bit for bit, on that same tree.
+#include <algorithm>
+#include <cfloat>
 #include <cstdio>
 #include <cstring>
 #include <string>

@@ -5,7 +5,10 @@
 
 // Mesh-walk offload of the wavefront kernel (wavefront_walk.cuh): the queues between shader CTAs and
 // walker CTAs, in global memory.  numWalkers == 0: the launch does not use it.
-#define TB_WF2_SLOTS 1024   // path slots per CTA of the wavefront kernel (= TB_WF2_PATHS, wavefront2.cuh)
+#ifndef TB_WF2_PATHS
+#define TB_WF2_PATHS 1024   // path slots per CTA of the wavefront kernel: a power of two <= 1024 (10-bit slot ids in the queue cells)
+#endif
+#define TB_WF2_SLOTS TB_WF2_PATHS
 struct WalkParams {
     uint4* reqRing;                // (1 << reqLog2) cells x 3 chunks of 16 bytes
     unsigned int reqLog2;

@@ -42,9 +42,6 @@
 #ifndef TB_WF2_THREADS_WIDE
 #define TB_WF2_THREADS_WIDE 768
 #endif
-#ifndef TB_WF2_PATHS
-#define TB_WF2_PATHS 1024      // must be a power of two <= 1024 (10-bit slot ids in the queue cells)
-#endif
 #ifndef TB_WF2_CTAS_PER_SM
 #define TB_WF2_CTAS_PER_SM 1
 #endif
@@ -563,9 +560,9 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             p = __shfl_sync(0xffffffffu, p, 0);
             if (offload) {
                 // sweep over six sources: T, answers(ext), A, answers(shadow), B, R
-                for (int k = 0; k < 12 && stage < 0; ++k) {
+                for (int k = 0; k < WALK_SWEEP_PASSES * 6 && stage < 0; ++k) {
                     const int pos = (p + k) % 6;
-                    const int minCount = k < 6 ? 32 : 1;
+                    const int minCount = k < 6 ? 32 : (k < 12 ? WALK_PARTIAL_MIN : 1);
                     if (pos == 1 || pos == 3) {
                         n = wf2_claim_answers(S, P.walk, pos == 1 ? WALK_KIND_EXT : WALK_KIND_SHADOW, minCount, ans0, ans1, ans2);
                         if (n > 0) {

@@ -34,6 +34,20 @@
 // are detected and redone with the reference-order walk (trace_ordered), as the scene program does.
 #pragma once
 
+// second pass of a shader warp's sweep over its work sources takes chunks of at least this many entries
+// (the first pass wants full chunks of 32, a third pass takes anything)
+#ifndef WALK_PARTIAL_MIN
+#define WALK_PARTIAL_MIN 1
+#endif
+#if WALK_PARTIAL_MIN > 1
+#define WALK_SWEEP_PASSES 3
+#else
+#define WALK_SWEEP_PASSES 2
+#endif
+#ifndef WALK_BOX_MIN
+#define WALK_BOX_MIN 20       // the BOX phase repeats while at least this many lanes have an interior node
+#endif
+
 #define WALK_KIND_EXT 0
 #define WALK_KIND_SHADOW 1
 // spin budget of the watchdogs (iterations of a ~0.5 us sleep): a launch that makes no progress for
@@ -87,6 +101,34 @@ struct WalkHit {
 
 TB_DEV uint32_t walk_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// a generic address the compiler cannot trace back to shared memory: loads through it are generic loads
+// (LD), so one instruction serves lanes that read the staged treelet and lanes that read global memory
+TB_DEV const unsigned char* walk_opaque(const void* p)
+{
+    unsigned long long a = (unsigned long long)p;
+    asm volatile("" : "+l"(a));
+    return reinterpret_cast<const unsigned char*>(a);
+}
+
+#ifdef WALK_FAST_SLAB
+// IntersectRayAABBFast (intersection.h:373-397) with hardware min/max (FMNMX) instead of the reference's
+// `a < b ? a : b` selects.  The two differ only when a product is NaN (0 * inf: a ray parallel to a slab
+// AND starting exactly on one of its planes) -- signed zeros compare equal everywhere the result is
+// used -- so `exact` comes back false for those lanes and the caller redoes the test the slow way.
+TB_DEV bool ray_aabb_fast(V3 pos, V3 rcp, float lx, float ly, float lz, float ux, float uy, float uz, float& t, bool& exact)
+{
+    const float a1 = (lx - pos.x) * rcp.x, a2 = (ux - pos.x) * rcp.x;
+    const float b1 = (ly - pos.y) * rcp.y, b2 = (uy - pos.y) * rcp.y;
+    const float c1 = (lz - pos.z) * rcp.z, c2 = (uz - pos.z) * rcp.z;
+    const float lmin = fmaxf(fmaxf(fminf(a1, a2), fminf(b1, b2)), fminf(c1, c2));
+    const float lmax = fminf(fminf(fmaxf(a1, a2), fmaxf(b1, b2)), fmaxf(c1, c2));
+    const float sum = ((a1 + a2) + (b1 + b2)) + (c1 + c2);   // NaN if any product is (and for inf - inf: a harmless false alarm)
+    exact = sum == sum;
+    t = lmin;
+    return (lmax >= 0.f) & (lmax >= lmin);
+}
+#endif
+
 // One CTA of walkers.  Shared memory: [0,16) mbarrier, then the traversal stacks (32 entries per
 // thread, entry-major so that a warp's accesses fall into 32 different banks), then the treelet.
 template <int THREADS>
@@ -127,6 +169,7 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
                          : "memory");
     }
     uint32_t* stack = stackBase + tid;   // entry k of this thread: stack[k * THREADS]
+    const unsigned char* treeletBytes = walk_opaque(treelet);
 
     // ---- per-lane state -------------------------------------------------------------------------------
     enum { PH_IDLE = 0, PH_TICKET = 1, PH_WALK = 2, PH_RETIRED = 3 };
@@ -174,38 +217,56 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
             if (nBox == 0) break;
             if (wBox) {
                 // IntersectRayMesh interior step, intersection.h:702-727
-                const BvhPair* pr = (meshId == W.treeletMesh && cur < (uint32_t)treeletPairs) ? treelet + cur : pairs + cur;
+                const unsigned char* recBase = (meshId == W.treeletMesh && cur < (uint32_t)treeletPairs)
+                                                   ? treeletBytes : reinterpret_cast<const unsigned char*>(pairs);
+                const BvhPair* pr = reinterpret_cast<const BvhPair*>(recBase + (size_t)cur * sizeof(BvhPair));
                 const float4 a = pr->a, b = pr->b, c = pr->c;
                 const uint2 kids = *reinterpret_cast<const uint2*>(&pr->left);
                 float tLeft, tRight;
+#ifdef WALK_FAST_SLAB
+                bool exL, exR;
+                bool hitLeft = ray_aabb_fast(o, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft, exL);
+                bool hitRight = ray_aabb_fast(o, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight, exR);
+                if (!(exL && exR)) {
+                    hitLeft = ray_aabb(o, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft);
+                    hitRight = ray_aabb(o, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight);
+                }
+                hitLeft = hitLeft && tLeft < tmax;
+                hitRight = hitRight && tRight < tmax;
+#else
                 const bool hitLeft = ray_aabb(o, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft) && tLeft < tmax;
                 const bool hitRight = ray_aabb(o, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight) && tRight < tmax;
+#endif
                 // "traverse closest first": the reference pushes the far child, then the near one, and pops the near
                 // one at once (intersection.h:716-727) -- the near child is `nxt`, the far one goes on the stack
                 const bool both = hitLeft && hitRight;
                 const bool swap = both && (tLeft < tRight);
                 const uint32_t far = swap ? kids.y : kids.x;              // what the reference pushes first
-                uint32_t nxt = both ? (swap ? kids.x : kids.y) : (hitLeft ? kids.x : kids.y);
-                if (both) {
-                    if (sp < TB_STACK) stack[sp * THREADS] = far;   // a deeper tree overflows the reference's own stack[32]: the host refuses it
-                    sp += 1;
-                }
-                if (!(hitLeft || hitRight)) {
-                    nxt = EMPTY;
-                    if (sp > 0) {
-                        sp -= 1;
-                        nxt = stack[sp * THREADS];
-                    }
-                }
-                if (nxt != EMPTY && (nxt & TB_LEAF) != 0u && pend == EMPTY) {
+                const uint32_t near = both ? (swap ? kids.x : kids.y) : (hitLeft ? kids.x : kids.y);
+                const bool any = hitLeft || hitRight;
+                // Stack traffic without divergent branches.  What this step can do: push `far` (both hit); pop
+                // (nothing hit); park a triangle in `pend` and pop what the reference would visit after testing
+                // it.  At most one push and two pops, of which the first pop can only return `far` itself when
+                // there was a push -- so memory sees one store (the entry that survives) and two loads.
+                const uint32_t top1 = sp > 0 ? stack[(sp - 1) * THREADS] : EMPTY;
+                const uint32_t top2 = sp > 1 ? stack[(sp - 2) * THREADS] : EMPTY;
+                // value sequence of pops after this step's push: p1, p2
+                const uint32_t p1 = both ? far : top1;
+                const uint32_t p2 = both ? top1 : top2;
+                uint32_t nxt = any ? near : p1;          // nothing hit: pop
+                int pops = any ? 0 : 1;
+                const bool park = nxt != EMPTY && (nxt & TB_LEAF) != 0u && pend == EMPTY;
+                if (park) {
                     // park the triangle, go on with what the reference would pop after testing it
                     pend = nxt;
-                    nxt = EMPTY;
-                    if (sp > 0) {
-                        sp -= 1;
-                        nxt = stack[sp * THREADS];
-                    }
+                    nxt = pops == 0 ? p1 : p2;
+                    pops += 1;
                 }
+                // net effect on the stack: +1 (push) - pops, never below zero (a pop from an empty stack returned EMPTY)
+                const int depthAfterPush = sp + (both ? 1 : 0);
+                const int newSp = depthAfterPush - pops < 0 ? 0 : depthAfterPush - pops;
+                if (both && newSp > sp && sp < TB_STACK) stack[sp * THREADS] = far;   // the pushed entry survives this step
+                sp = newSp;
                 cur = nxt;
             }
             if (nBox < 20) break;   // give the other phases a turn (one step per turn keeps every lane progressing)
