@@ -323,6 +323,19 @@ const tb200_mesh* tb200_mesh_bin_mesh(const tb200_mesh_file* f);
 int tb200_mesh_bin_save(const char* path, const tb200_mesh* mesh);  /* 0 on success */
 void tb200_mesh_bin_free(tb200_mesh_file* f);
 
+/* ---- scene cache (".tcache") -------------------------------------------------------------------------
+ * Everything tb200_create derives from a tb200_scene -- primitive records with their hoisted constants,
+ * child-pair BVH records in breadth-first order, pre-gathered triangles and vertex normals, the flat scene
+ * program, and the probe WITH its four sampling tables (Probe::BuildCDF, src/probe.h:31-79) -- stored in
+ * exactly the layouts the device holds, so that tb200_create_cached goes from the file to device memory
+ * array by array: no .tin/OBJ loader, no BVH builder, no re-packing, no per-triangle gather, no BuildCDF.
+ * It plays the role the reference gives its `.bin` mesh cache (src/mesh.cpp:809-880, `tinsel -convert`,
+ * src/main.cpp:151-169), for the whole scene.  The file is this build's device layout, not an interchange
+ * format: a file written by another build is refused (layout stamp) and the caller uses tb200_create.
+ * tb200_scene_cache_save needs no GPU.  A renderer from a cache is bit-identical to one from the scene. */
+int tb200_scene_cache_save(const tb200_scene* scene, const char* path);   /* 0 on success */
+tb200_renderer* tb200_create_cached(const char* path, int device);         /* NULL on failure (tb200_last_error) */
+
 /* ---- mesh BVH construction on the GPU ---------------------------------------------------------------
  * Replaces Mesh::RebuildBVH + BVHBuilder::Build (src/mesh.cpp:314-338, src/bvh.h:30-263: one Bounds per
  * triangle, recursive full-sweep SAH on one host core, 1.33 s for ajax) for triangle meshes: a PLOC

@@ -88,6 +88,10 @@ def load_library():
     lib.tb200_destroy.argtypes = [C.c_void_p]
     lib.tb200_last_error.restype = C.c_char_p
     lib.tb200_last_error.argtypes = []
+    lib.tb200_scene_cache_save.restype = C.c_int
+    lib.tb200_scene_cache_save.argtypes = [C.POINTER(Scene), C.c_char_p]
+    lib.tb200_create_cached.restype = C.c_void_p
+    lib.tb200_create_cached.argtypes = [C.c_char_p, C.c_int]
     lib.tb200_bvh_build.restype = C.c_int
     lib.tb200_bvh_build.argtypes = [f32p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_int, C.POINTER(abi.BvhBuildInfo)]
     lib.tb200_bvh_build_error.restype = C.c_char_p
@@ -103,6 +107,12 @@ def last_error():
 
 def sample_seed(pixel, frame):
     return load_library().tb200_sample_seed(pixel, frame)
+
+
+def scene_cache_save(scene, path):
+    """Writes the device-layout scene cache of `scene` (tb200_scene_cache_save; no GPU needed)."""
+    if load_library().tb200_scene_cache_save(scene, path.encode()) != 0:
+        raise TinselB200Error("tb200_scene_cache_save failed: " + last_error())
 
 
 def bvh_build(positions, indices, nodes, device=0):
@@ -165,10 +175,13 @@ class Renderer:
                                    receives the running sums (sum w*rgb, sum w)
     """
 
-    def __init__(self, scene, device=0, devices=None):
-        """devices: a list of CUDA ordinals -> one renderer spread over several GPUs (tb200_create_multi)."""
+    def __init__(self, scene, device=0, devices=None, cache=None):
+        """devices: a list of CUDA ordinals -> one renderer spread over several GPUs (tb200_create_multi).
+        cache: path of a scene cache written by scene_cache_save (tb200_create_cached); `scene` is ignored."""
         self.lib = load_library()
-        if devices is not None:
+        if cache is not None:
+            self.h = self.lib.tb200_create_cached(cache.encode(), device)
+        elif devices is not None:
             arr = (C.c_int * len(devices))(*devices)
             self.h = self.lib.tb200_create_multi(scene, arr, len(devices))
         else:

@@ -157,6 +157,8 @@ EXPORTS = [
     "tb200_bvh_build",
     "tb200_bvh_build_error",
     "tb200_create_multi",
+    "tb200_create_cached",
+    "tb200_scene_cache_save",
     "tb200_num_devices",
     "tb200_slab_rows",
     "tb200_slab_traced_rows",

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cstdio>
@@ -407,12 +408,152 @@ void free_device(tb200_renderer* r)
     r->dRadiance = r->dRaster = nullptr;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Scene image: everything build_scene() derives from a tb200_scene, in exactly the layouts the device
+// holds -- DPrim records with their hoisted constants, child-pair BVH records in breadth-first order,
+// pre-gathered triangles, the flat scene program, the probe with its four sampling tables.  It is
+// built on the host (no GPU needed), uploaded array by array, and it is what the scene cache stores
+// (tb200_scene_cache_save / tb200_create_cached): a cached scene goes from the file to the device
+// without the loader, the BVH re-packing, the per-triangle gather or Probe::BuildCDF.
+// ---------------------------------------------------------------------------------------------------
+struct MeshImage {
+    std::vector<BvhPair> pairs;
+    std::vector<float4> verts, norms;
+    std::vector<float> cdf;
+    int numTris = 0;
+    uint32_t rootRef = TB_LEAF;
+    int depth = 0;
+};
+
+struct SceneImage {
+    std::vector<DPrim> prims;
+    std::vector<BvhPair> scenePairs;
+    uint32_t sceneRoot = TB_LEAF;
+    std::vector<ProgOp> flat;
+    std::vector<MeshImage> meshes;
+    V3 horizon = v3s(0.0f), zenith = v3s(0.0f);
+    int numNee = 0;
+    // scheduling hints: the largest mesh, and its primitive's world bounds (its leaf of the scene BVH)
+    int maxTris = 0;
+    int splitBoxValid = 0;
+    V3 splitLo = v3s(0.0f), splitHi = v3s(0.0f);
+    // probe (src/probe.h:9-86), each table with one element of slack (see below)
+    int probeValid = 0, probeW = 0, probeH = 0;
+    std::vector<float4> probeData;
+    std::vector<float> pdfX, cdfX, pdfY, cdfY;
+};
+
+bool image_from_scene(const tb200_scene* s, SceneImage* img)
+{
+    // meshes: pairs + pre-gathered triangles
+    img->meshes.resize(s->numMeshes);
+    for (int m = 0; m < s->numMeshes; ++m) {
+        const tb200_mesh& g = s->meshes[m];
+        MeshImage& mi = img->meshes[m];
+        mi.rootRef = build_pairs(g.nodes, g.numNodes, &mi.pairs, &mi.depth);
+        const int numTris = g.numIndices / 3;
+        mi.numTris = numTris;
+        img->maxTris = std::max(img->maxTris, numTris);
+        mi.verts.resize(size_t(numTris) * 3);
+        mi.norms.resize(size_t(numTris) * 3);
+        for (int t = 0; t < numTris; ++t) {
+            const int i0 = g.indices[t * 3 + 0], i1 = g.indices[t * 3 + 1], i2 = g.indices[t * 3 + 2];
+            const float* a = g.positions + size_t(i0) * 3;
+            const float* b = g.positions + size_t(i1) * 3;
+            const float* c = g.positions + size_t(i2) * 3;
+            mi.verts[size_t(t) * 3 + 0] = make_float4(a[0], a[1], a[2], b[0]);
+            mi.verts[size_t(t) * 3 + 1] = make_float4(b[1], b[2], c[0], c[1]);
+            mi.verts[size_t(t) * 3 + 2] = make_float4(c[2], 0.0f, 0.0f, 0.0f);
+            const float* n1 = g.normals + size_t(i0) * 3;
+            const float* n2 = g.normals + size_t(i1) * 3;
+            const float* n3 = g.normals + size_t(i2) * 3;
+            mi.norms[size_t(t) * 3 + 0] = make_float4(n1[0], n1[1], n1[2], n2[0]);
+            mi.norms[size_t(t) * 3 + 1] = make_float4(n2[1], n2[2], n3[0], n3[1]);
+            mi.norms[size_t(t) * 3 + 2] = make_float4(n3[2], 0.0f, 0.0f, 0.0f);
+        }
+        mi.cdf.assign(size_t(numTris), 0.0f);   // only read when the mesh is sampled as a light
+        if (g.cdf) memcpy(mi.cdf.data(), g.cdf, size_t(numTris) * sizeof(float));
+    }
+    // the largest mesh's primitive and its world bounds = that primitive's leaf in the scene BVH
+    {
+        int bigPrim = -1, bigTris = 0;
+        for (int i = 0; i < s->numPrimitives; ++i) {
+            const tb200_primitive& p = s->primitives[i];
+            if (p.type == TB200_MESH && p.mesh >= 0 && p.mesh < s->numMeshes && s->meshes[p.mesh].numIndices / 3 > bigTris) {
+                bigTris = s->meshes[p.mesh].numIndices / 3;
+                bigPrim = i;
+            }
+        }
+        for (int n = 0; n < s->numBvhNodes && bigPrim >= 0; ++n) {
+            const tb200_bvh_node& node = s->bvhNodes[n];
+            if ((node.right_leaf >> 31) != 0 && (int)node.left == bigPrim) {
+                img->splitLo = v3(node.lower[0], node.lower[1], node.lower[2]);
+                img->splitHi = v3(node.upper[0], node.upper[1], node.upper[2]);
+                img->splitBoxValid = 1;
+                break;
+            }
+        }
+    }
+
+    // primitives
+    img->prims.resize(s->numPrimitives);
+    img->numNee = s->sky.probeValid ? 1 : 0;
+    for (int i = 0; i < s->numPrimitives; ++i) {
+        const tb200_primitive& p = s->primitives[i];
+        DPrim& d = img->prims[i];
+        memset(&d, 0, sizeof(d));
+        d.start = to_xf(p.start);
+        d.end = to_xf(p.end);
+        d.isStatic = memcmp(&p.start, &p.end, sizeof(tb200_transform)) == 0;
+        // with start == end, Lerp(a,b,t) = a + (b-a)*t = a + 0*t is time independent
+        d.fixed = interpolate_transform(d.start, d.end, 0.0f);
+        d.type = p.type;
+        d.radius = p.radius;
+        memcpy(d.plane, p.plane, 16);
+        d.mesh = p.mesh;
+        d.lightSamples = p.lightSamples;
+        if (p.type == TB200_MESH && (p.mesh < 0 || p.mesh >= s->numMeshes)) return set_error("primitive references a missing mesh");
+        // PrimitiveArea, intersection.h:833-853
+        if (p.type == TB200_SPHERE)
+            d.area = 4.0f * TB_PI * p.radius * p.radius;
+        else if (p.type == TB200_MESH)
+            d.area = s->meshes[p.mesh].area * p.end.s;
+        else
+            d.area = 0.0f;
+        d.mat = make_material(p.material);
+        if (p.lightSamples > 0) img->numNee += p.lightSamples;
+    }
+    img->sceneRoot = build_pairs(s->bvhNodes, s->numBvhNodes, &img->scenePairs);
+    build_program(s, &img->flat);
+    img->horizon = hv3(s->sky.horizon);
+    img->zenith = hv3(s->sky.zenith);
+    if (s->sky.probeValid) {
+        const size_t n = size_t(s->sky.probeWidth) * s->sky.probeHeight;
+        img->probeValid = 1;
+        img->probeW = s->sky.probeWidth;
+        img->probeH = s->sky.probeHeight;
+        // one element of slack after each table: ProbeSample's column search may land on
+        // col == width (probe.h:217-220) and read one past the last row
+        img->probeData.assign(n + 1, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        memcpy(img->probeData.data(), s->sky.probeData, n * 16);
+        img->pdfX.assign(n + 1, 0.0f);
+        img->cdfX.assign(n + 1, 0.0f);
+        img->pdfY.assign(size_t(s->sky.probeHeight) + 1, 0.0f);
+        img->cdfY.assign(size_t(s->sky.probeHeight) + 1, 0.0f);
+        memcpy(img->pdfX.data(), s->sky.pdfValuesX, n * 4);
+        memcpy(img->cdfX.data(), s->sky.cdfValuesX, n * 4);
+        memcpy(img->pdfY.data(), s->sky.pdfValuesY, size_t(s->sky.probeHeight) * 4);
+        memcpy(img->cdfY.data(), s->sky.cdfValuesY, size_t(s->sky.probeHeight) * 4);
+    }
+    return true;
+}
+
 // Mesh-walk offload (wavefront_walk.cuh): decided per scene.  Eligible: free-running scenes whose scene
 // level runs as the flat program (<= 16 primitives) and that hold a mesh of more than 4096 triangles whose
 // BVH is no deeper than the reference's own traversal stack (a deeper tree overflows `int stack[32]`,
 // intersection.h:688, in the reference itself).  TINSEL_B200_OFFLOAD=0 turns it off, =1 offloads every
 // mesh (tests); TINSEL_B200_WALKERS=n sets the number of walker CTAs.
-bool setup_offload(tb200_renderer* r, const tb200_scene* s)
+bool setup_offload(tb200_renderer* r, const SceneImage& img)
 {
     DScene& sc = r->scene;
     sc.deferMask = 0u;
@@ -421,16 +562,16 @@ bool setup_offload(tb200_renderer* r, const tb200_scene* s)
     r->walk.treeletMesh = -1;
     const char* env = getenv("TINSEL_B200_OFFLOAD");
     const bool force = env && atoi(env) == 1;
-    if ((env && atoi(env) == 0) || r->hardPhases || sc.numFlat <= 0 || s->numPrimitives > 16) return true;
+    if ((env && atoi(env) == 0) || r->hardPhases || sc.numFlat <= 0 || img.prims.size() > 16) return true;
     int bigMesh = -1, bigTris = 0;
-    for (int i = 0; i < s->numPrimitives; ++i) {
-        const tb200_primitive& p = s->primitives[i];
+    for (size_t i = 0; i < img.prims.size(); ++i) {
+        const DPrim& p = img.prims[i];
         if (p.type != TB200_MESH) continue;
-        const int tris = s->meshes[p.mesh].numIndices / 3;
-        if ((tris > 4096 || force) && r->meshDepth[p.mesh] <= TB_STACK) {
+        const MeshImage& mi = img.meshes[p.mesh];
+        if ((mi.numTris > 4096 || force) && mi.depth <= TB_STACK) {
             sc.deferMask |= 1u << i;
-            if (tris > bigTris) {
-                bigTris = tris;
+            if (mi.numTris > bigTris) {
+                bigTris = mi.numTris;
                 bigMesh = p.mesh;
             }
         }
@@ -438,7 +579,7 @@ bool setup_offload(tb200_renderer* r, const tb200_scene* s)
     if (sc.deferMask == 0u) return true;
 
     // queues: a request ring with more cells than the device has path slots (one request per slot at most),
-    // two answer rings of TB_WF2_PATHS cells per shader CTA, a handful of counters
+    // two answer rings of TB_WF2_SLOTS cells per shader CTA, a handful of counters
     const int ctas = std::max(1, r->numSMs);
     unsigned int log2 = 10;
     while ((1ull << log2) < (unsigned long long)ctas * TB_WF2_SLOTS) ++log2;
@@ -460,7 +601,7 @@ bool setup_offload(tb200_renderer* r, const tb200_scene* s)
     W.abortFlag = ctr + 4;
     W.ansTail = ctr + 16;
     W.treeletMesh = bigMesh;
-    W.treeletPairs = bigMesh >= 0 ? r->meshPairs[bigMesh] : 0;
+    W.treeletPairs = bigMesh >= 0 ? (int)img.meshes[bigMesh].pairs.size() : 0;
     const char* nw = getenv("TINSEL_B200_WALKERS");
     r->numWalkers = nw ? atoi(nw) : (ctas * 3) / 8;
     r->numWalkers = std::max(1, std::min(r->numWalkers, ctas - 1));
@@ -483,46 +624,19 @@ bool check_offload(tb200_renderer* r)
                                 : "mesh-walk offload: a walker CTA waited for requests without progress (watchdog); the frame is incomplete");
 }
 
-bool build_scene(tb200_renderer* r, const tb200_scene* s)
+// device upload of a scene image + the per-scene scheduling decisions (which read the environment)
+bool upload_image(tb200_renderer* r, const SceneImage& img)
 {
     uint64_t* h2d = &r->stats.h2dBytes;
     memset(&r->scene, 0, sizeof(r->scene));
-
-    // meshes: pairs + pre-gathered triangles
-    std::vector<DMesh> meshes(s->numMeshes);
-    r->meshDepth.clear();
-    r->meshPairs.clear();
-    for (int m = 0; m < s->numMeshes; ++m) {
-        const tb200_mesh& g = s->meshes[m];
-        std::vector<BvhPair> pairs;
-        int depth = 0;
-        const uint32_t root = build_pairs(g.nodes, g.numNodes, &pairs, &depth);
-        r->meshDepth.push_back(depth);
-        r->meshPairs.push_back((int)pairs.size());
-        const int numTris = g.numIndices / 3;
-        std::vector<float4> verts(size_t(numTris) * 3), norms(size_t(numTris) * 3);
-        for (int t = 0; t < numTris; ++t) {
-            const int i0 = g.indices[t * 3 + 0], i1 = g.indices[t * 3 + 1], i2 = g.indices[t * 3 + 2];
-            const float* a = g.positions + size_t(i0) * 3;
-            const float* b = g.positions + size_t(i1) * 3;
-            const float* c = g.positions + size_t(i2) * 3;
-            verts[size_t(t) * 3 + 0] = make_float4(a[0], a[1], a[2], b[0]);
-            verts[size_t(t) * 3 + 1] = make_float4(b[1], b[2], c[0], c[1]);
-            verts[size_t(t) * 3 + 2] = make_float4(c[2], 0.0f, 0.0f, 0.0f);
-            const float* n1 = g.normals + size_t(i0) * 3;
-            const float* n2 = g.normals + size_t(i1) * 3;
-            const float* n3 = g.normals + size_t(i2) * 3;
-            norms[size_t(t) * 3 + 0] = make_float4(n1[0], n1[1], n1[2], n2[0]);
-            norms[size_t(t) * 3 + 1] = make_float4(n2[1], n2[2], n3[0], n3[1]);
-            norms[size_t(t) * 3 + 2] = make_float4(n3[2], 0.0f, 0.0f, 0.0f);
-        }
-        std::vector<float> cdf(size_t(numTris), 0.0f);   // only read when the mesh is sampled as a light
-        if (g.cdf) memcpy(cdf.data(), g.cdf, size_t(numTris) * sizeof(float));
+    std::vector<DMesh> meshes(img.meshes.size());
+    for (size_t m = 0; m < img.meshes.size(); ++m) {
+        const MeshImage& mi = img.meshes[m];
         BvhPair* dPairs;
         float4 *dVerts, *dNorms;
         float* dCdf;
-        if (!upload(pairs, &dPairs, h2d) || !upload(verts, &dVerts, h2d) || !upload(norms, &dNorms, h2d) ||
-            !upload(cdf, &dCdf, h2d))
+        if (!upload(mi.pairs, &dPairs, h2d) || !upload(mi.verts, &dVerts, h2d) || !upload(mi.norms, &dNorms, h2d) ||
+            !upload(mi.cdf, &dCdf, h2d))
             return false;
         r->owned.push_back(dPairs);
         r->owned.push_back(dVerts);
@@ -532,8 +646,8 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
         meshes[m].triVerts = dVerts;
         meshes[m].triNormals = dNorms;
         meshes[m].cdf = dCdf;
-        meshes[m].numTris = numTris;
-        meshes[m].rootRef = root;
+        meshes[m].numTris = mi.numTris;
+        meshes[m].rootRef = mi.rootRef;
     }
     if (!upload(meshes, &r->dMeshes, h2d)) return false;
     // Scheduling mode of the wavefront kernel (measured, profiles/README.md): block-synchronous
@@ -542,40 +656,21 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
     // free-running warps win otherwise, and by a wide margin when ray cost varies (deep mesh BVHs).
     // TINSEL_B200_SCHED=hard|free overrides.
     {
-        int maxTris = 0;
-        for (int m = 0; m < s->numMeshes; ++m) maxTris = std::max(maxTris, s->meshes[m].numIndices / 3);
-        int numNee = s->sky.probeValid ? 1 : 0;
-        for (int i = 0; i < s->numPrimitives; ++i)
-            if (s->primitives[i].lightSamples > 0) numNee += s->primitives[i].lightSamples;
-        r->hardPhases = (numNee > 1 && maxTris <= 4096) ? 1 : 0;
+        r->hardPhases = (img.numNee > 1 && img.maxTris <= 4096) ? 1 : 0;
         const char* sched = getenv("TINSEL_B200_SCHED");
         if (sched && strcmp(sched, "hard") == 0) r->hardPhases = 1;
         if (sched && strcmp(sched, "free") == 0) r->hardPhases = 0;
         // CTA size: deep mesh BVHs make traversal latency bound (L2 hits), which more warps hide; on
         // scenes held in shared memory more warps only thrash the instruction cache.  TINSEL_B200_CTA=512|768.
-        r->wideCta = (!r->hardPhases && maxTris > 4096) ? 1 : 0;
+        r->wideCta = (!r->hardPhases && img.maxTris > 4096) ? 1 : 0;
         // Split trace queue: rays entering the largest mesh's world bounds are queued apart from the
-        // rest (scheduling only).  Bounds come from that primitive's leaf in the scene BVH.
+        // rest (scheduling only).
         r->scene.splitValid = 0;
         const char* split = getenv("TINSEL_B200_SPLIT");   // 0: never, 1: whenever the scene has a mesh (tests)
-        if (maxTris > 4096 || (split && atoi(split) == 1)) {
-            int bigPrim = -1, bigTris = 0;
-            for (int i = 0; i < s->numPrimitives; ++i) {
-                const tb200_primitive& p = s->primitives[i];
-                if (p.type == TB200_MESH && p.mesh >= 0 && p.mesh < s->numMeshes && s->meshes[p.mesh].numIndices / 3 > bigTris) {
-                    bigTris = s->meshes[p.mesh].numIndices / 3;
-                    bigPrim = i;
-                }
-            }
-            for (int n = 0; n < s->numBvhNodes && bigPrim >= 0; ++n) {
-                const tb200_bvh_node& node = s->bvhNodes[n];
-                if ((node.right_leaf >> 31) != 0 && (int)node.left == bigPrim) {
-                    r->scene.splitLo = v3(node.lower[0], node.lower[1], node.lower[2]);
-                    r->scene.splitHi = v3(node.upper[0], node.upper[1], node.upper[2]);
-                    r->scene.splitValid = 1;
-                    break;
-                }
-            }
+        if ((img.maxTris > 4096 || (split && atoi(split) == 1)) && img.splitBoxValid) {
+            r->scene.splitLo = img.splitLo;
+            r->scene.splitHi = img.splitHi;
+            r->scene.splitValid = 1;
         }
         if (split && atoi(split) == 0) r->scene.splitValid = 0;
         r->tunePhase = (r->scene.splitValid && !split && !r->hardPhases) ? 0 : 3;   // an explicit TINSEL_B200_SPLIT is final
@@ -583,71 +678,31 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
         if (cta && atoi(cta) == 768) r->wideCta = 1;
         if (cta && atoi(cta) == 512) r->wideCta = 0;
     }
-
-    // primitives
-    std::vector<DPrim> prims(s->numPrimitives);
-    int numNee = s->sky.probeValid ? 1 : 0;
-    for (int i = 0; i < s->numPrimitives; ++i) {
-        const tb200_primitive& p = s->primitives[i];
-        DPrim& d = prims[i];
-        memset(&d, 0, sizeof(d));
-        d.start = to_xf(p.start);
-        d.end = to_xf(p.end);
-        d.isStatic = memcmp(&p.start, &p.end, sizeof(tb200_transform)) == 0;
-        // with start == end, Lerp(a,b,t) = a + (b-a)*t = a + 0*t is time independent
-        d.fixed = interpolate_transform(d.start, d.end, 0.0f);
-        d.type = p.type;
-        d.radius = p.radius;
-        memcpy(d.plane, p.plane, 16);
-        d.mesh = p.mesh;
-        d.lightSamples = p.lightSamples;
-        // PrimitiveArea, intersection.h:833-853
-        if (p.type == TB200_SPHERE)
-            d.area = 4.0f * TB_PI * p.radius * p.radius;
-        else if (p.type == TB200_MESH)
-            d.area = s->meshes[p.mesh].area * p.end.s;
-        else
-            d.area = 0.0f;
-        d.mat = make_material(p.material);
-        if (p.type == TB200_MESH && (p.mesh < 0 || p.mesh >= s->numMeshes)) return set_error("primitive references a missing mesh");
-        if (p.lightSamples > 0) numNee += p.lightSamples;
-    }
-    if (!upload(prims, &r->dPrims, h2d)) return false;
-
-    std::vector<BvhPair> scenePairs;
-    const uint32_t sceneRoot = build_pairs(s->bvhNodes, s->numBvhNodes, &scenePairs);
-    if (!upload(scenePairs, &r->dScenePairs, h2d)) return false;
+    if (!upload(img.prims, &r->dPrims, h2d)) return false;
+    if (!upload(img.scenePairs, &r->dScenePairs, h2d)) return false;
 
     DScene& sc = r->scene;
     sc.prims = r->dPrims;
-    sc.numPrims = s->numPrimitives;
+    sc.numPrims = (int)img.prims.size();
     sc.pairs = r->dScenePairs;
-    sc.numPairs = (int)scenePairs.size();
-    std::vector<ProgOp> flat;
-    if (!getenv("TINSEL_B200_NO_FLAT")) build_program(s, &flat);
+    sc.numPairs = (int)img.scenePairs.size();
+    static const std::vector<ProgOp> noFlat;
+    const std::vector<ProgOp>& flat = getenv("TINSEL_B200_NO_FLAT") ? noFlat : img.flat;
     if (!upload(flat, &r->dFlat, h2d)) return false;
     sc.flat = r->dFlat;
     sc.numFlat = (int)flat.size();
-    if (!setup_offload(r, s)) return false;
-    sc.rootRef = sceneRoot;
+    if (!setup_offload(r, img)) return false;
+    sc.rootRef = img.sceneRoot;
     sc.meshes = r->dMeshes;
-    sc.numMeshes = s->numMeshes;
-    sc.horizon = hv3(s->sky.horizon);
-    sc.zenith = hv3(s->sky.zenith);
-    sc.numNee = numNee;
-    if (s->sky.probeValid) {
-        const size_t n = size_t(s->sky.probeWidth) * s->sky.probeHeight;
-        // one element of slack after each table: ProbeSample's column search may land on
-        // col == width (probe.h:217-220) and read one past the last row
-        std::vector<float4> data(n);
-        memcpy(data.data(), s->sky.probeData, n * 16);
-        std::vector<float> pdfX(s->sky.pdfValuesX, s->sky.pdfValuesX + n), cdfX(s->sky.cdfValuesX, s->sky.cdfValuesX + n);
-        std::vector<float> pdfY(s->sky.pdfValuesY, s->sky.pdfValuesY + s->sky.probeHeight);
-        std::vector<float> cdfY(s->sky.cdfValuesY, s->sky.cdfValuesY + s->sky.probeHeight);
+    sc.numMeshes = (int)img.meshes.size();
+    sc.horizon = img.horizon;
+    sc.zenith = img.zenith;
+    sc.numNee = img.numNee;
+    if (img.probeValid) {
         float4* dData;
         float *dPdfX, *dCdfX, *dPdfY, *dCdfY;
-        if (!upload(data, &dData, h2d, 1) || !upload(pdfX, &dPdfX, h2d, 1) || !upload(cdfX, &dCdfX, h2d, 1) ||
-            !upload(pdfY, &dPdfY, h2d, 1) || !upload(cdfY, &dCdfY, h2d, 1))
+        if (!upload(img.probeData, &dData, h2d) || !upload(img.pdfX, &dPdfX, h2d) || !upload(img.cdfX, &dCdfX, h2d) ||
+            !upload(img.pdfY, &dPdfY, h2d) || !upload(img.cdfY, &dCdfY, h2d))
             return false;
         r->owned.push_back(dData);
         r->owned.push_back(dPdfX);
@@ -655,13 +710,138 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
         r->owned.push_back(dPdfY);
         r->owned.push_back(dCdfY);
         sc.probe.valid = 1;
-        sc.probe.width = s->sky.probeWidth;
-        sc.probe.height = s->sky.probeHeight;
+        sc.probe.width = img.probeW;
+        sc.probe.height = img.probeH;
         sc.probe.data = dData;
         sc.probe.pdfX = dPdfX;
         sc.probe.cdfX = dCdfX;
         sc.probe.pdfY = dPdfY;
         sc.probe.cdfY = dCdfY;
+    }
+    return true;
+}
+
+bool build_scene(tb200_renderer* r, const tb200_scene* s)
+{
+    SceneImage img;
+    return image_from_scene(s, &img) && upload_image(r, img);
+}
+
+// ---- scene cache file ------------------------------------------------------------------------------
+// "TB2CACHE", a layout stamp (the records are this build's device structs, not an interchange format:
+// a stamp mismatch is refused and the caller falls back to tb200_create), then the SceneImage fields in
+// declaration order; every array as a 64-bit count followed by its bytes.
+const char kCacheMagic[8] = {'T', 'B', '2', 'C', 'A', 'C', 'H', 'E'};
+const uint32_t kCacheVersion = 2;
+
+struct CacheStamp {
+    uint32_t version, sizeofPrim, sizeofPair, sizeofOp;
+};
+
+template <typename T>
+bool put_vec(FILE* f, const std::vector<T>& v)
+{
+    const uint64_t n = v.size();
+    return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <typename T>
+bool put_pod(FILE* f, const T& v) { return fwrite(&v, sizeof(T), 1, f) == 1; }
+
+template <typename T>
+bool get_vec(FILE* f, std::vector<T>* v, uint64_t fileBytes)
+{
+    uint64_t n = 0;
+    if (fread(&n, 8, 1, f) != 1 || n > fileBytes / sizeof(T)) return false;   // a count can never exceed the file
+    v->resize(size_t(n));
+    return n == 0 || fread(v->data(), sizeof(T), size_t(n), f) == n;
+}
+template <typename T>
+bool get_pod(FILE* f, T* v) { return fread(v, sizeof(T), 1, f) == 1; }
+
+bool image_save(const SceneImage& img, const char* path)
+{
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_error(std::string("tb200_scene_cache_save: cannot open ") + path);
+    const CacheStamp stamp = {kCacheVersion, (uint32_t)sizeof(DPrim), (uint32_t)sizeof(BvhPair), (uint32_t)sizeof(ProgOp)};
+    bool ok = fwrite(kCacheMagic, 1, 8, f) == 8 && put_pod(f, stamp);
+    ok = ok && put_vec(f, img.prims) && put_vec(f, img.scenePairs) && put_pod(f, img.sceneRoot) && put_vec(f, img.flat);
+    const uint64_t numMeshes = img.meshes.size();
+    ok = ok && put_pod(f, numMeshes);
+    for (const MeshImage& m : img.meshes)
+        ok = ok && put_vec(f, m.pairs) && put_vec(f, m.verts) && put_vec(f, m.norms) && put_vec(f, m.cdf) && put_pod(f, m.numTris) &&
+             put_pod(f, m.rootRef) && put_pod(f, m.depth);
+    ok = ok && put_pod(f, img.horizon) && put_pod(f, img.zenith) && put_pod(f, img.numNee) && put_pod(f, img.maxTris) &&
+         put_pod(f, img.splitBoxValid) && put_pod(f, img.splitLo) && put_pod(f, img.splitHi);
+    ok = ok && put_pod(f, img.probeValid) && put_pod(f, img.probeW) && put_pod(f, img.probeH) && put_vec(f, img.probeData) &&
+         put_vec(f, img.pdfX) && put_vec(f, img.cdfX) && put_vec(f, img.pdfY) && put_vec(f, img.cdfY);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? true : set_error(std::string("tb200_scene_cache_save: write failed: ") + path);
+}
+
+bool image_load(const char* path, SceneImage* img)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(std::string("tb200_create_cached: cannot open ") + path);
+    fseek(f, 0, SEEK_END);
+    const uint64_t fileBytes = (uint64_t)std::max(0L, ftell(f));
+    fseek(f, 0, SEEK_SET);
+    char magic[8];
+    CacheStamp stamp;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kCacheMagic, 8) == 0 && get_pod(f, &stamp);
+    if (ok && (stamp.version != kCacheVersion || stamp.sizeofPrim != sizeof(DPrim) || stamp.sizeofPair != sizeof(BvhPair) ||
+               stamp.sizeofOp != sizeof(ProgOp))) {
+        fclose(f);
+        return set_error(std::string("tb200_create_cached: ") + path + " was written by another build of this library (layout stamp differs): recreate it");
+    }
+    ok = ok && get_vec(f, &img->prims, fileBytes) && get_vec(f, &img->scenePairs, fileBytes) && get_pod(f, &img->sceneRoot) &&
+         get_vec(f, &img->flat, fileBytes);
+    uint64_t numMeshes = 0;
+    ok = ok && get_pod(f, &numMeshes) && numMeshes <= fileBytes;
+    if (ok) img->meshes.resize(size_t(numMeshes));
+    for (size_t m = 0; ok && m < img->meshes.size(); ++m) {
+        MeshImage& mi = img->meshes[m];
+        ok = get_vec(f, &mi.pairs, fileBytes) && get_vec(f, &mi.verts, fileBytes) && get_vec(f, &mi.norms, fileBytes) &&
+             get_vec(f, &mi.cdf, fileBytes) && get_pod(f, &mi.numTris) && get_pod(f, &mi.rootRef) && get_pod(f, &mi.depth);
+    }
+    ok = ok && get_pod(f, &img->horizon) && get_pod(f, &img->zenith) && get_pod(f, &img->numNee) && get_pod(f, &img->maxTris) &&
+         get_pod(f, &img->splitBoxValid) && get_pod(f, &img->splitLo) && get_pod(f, &img->splitHi);
+    ok = ok && get_pod(f, &img->probeValid) && get_pod(f, &img->probeW) && get_pod(f, &img->probeH) && get_vec(f, &img->probeData, fileBytes) &&
+         get_vec(f, &img->pdfX, fileBytes) && get_vec(f, &img->cdfX, fileBytes) && get_vec(f, &img->pdfY, fileBytes) &&
+         get_vec(f, &img->cdfY, fileBytes);
+    fclose(f);
+    if (!ok) return set_error(std::string("tb200_create_cached: truncated or malformed cache file ") + path);
+    return true;
+}
+
+// every index a kernel will follow stays inside its array (a cache file is as untrusted as a tb200_scene)
+bool validate_image(const SceneImage& img, std::string* why)
+{
+    const size_t np = img.prims.size();
+    if (np == 0 || np > 4095) return *why = "bad primitive count", false;
+    auto ref_ok = [](uint32_t ref, size_t pairs, size_t items) { return (ref & TB_LEAF) ? (ref & ~TB_LEAF) < items : ref < pairs; };
+    if (!ref_ok(img.sceneRoot, img.scenePairs.size(), np)) return *why = "scene root reference out of range", false;
+    for (const BvhPair& p : img.scenePairs)
+        if (!ref_ok(p.left, img.scenePairs.size(), np) || !ref_ok(p.right, img.scenePairs.size(), np)) return *why = "scene BVH reference out of range", false;
+    for (const MeshImage& m : img.meshes) {
+        const size_t nt = (size_t)std::max(0, m.numTris);
+        if (nt == 0 || m.verts.size() != nt * 3 || m.norms.size() != nt * 3 || m.cdf.size() != nt) return *why = "mesh arrays do not match the triangle count", false;
+        if (!ref_ok(m.rootRef, m.pairs.size(), nt)) return *why = "mesh root reference out of range", false;
+        for (const BvhPair& p : m.pairs)
+            if (!ref_ok(p.left, m.pairs.size(), nt) || !ref_ok(p.right, m.pairs.size(), nt)) return *why = "mesh BVH reference out of range", false;
+    }
+    for (const DPrim& p : img.prims) {
+        if (p.type != TB200_SPHERE && p.type != TB200_PLANE && p.type != TB200_MESH) return *why = "unknown primitive type", false;
+        if (p.type == TB200_MESH && (p.mesh < 0 || (size_t)p.mesh >= img.meshes.size())) return *why = "primitive references a missing mesh", false;
+        if (p.lightSamples < 0 || p.lightSamples > 4095) return *why = "lightSamples out of range", false;
+    }
+    for (const ProgOp& op : img.flat)
+        if ((size_t)(op.kindPrim >> 8) >= np && (op.kindPrim & 0xff) != TB_OP_BOX) return *why = "scene program references a missing primitive", false;
+    if (img.flat.size() > 32) return *why = "scene program too long", false;
+    if (img.probeValid) {
+        const size_t n = (size_t)std::max(0, img.probeW) * (size_t)std::max(0, img.probeH);
+        if (n == 0 || img.probeData.size() != n + 1 || img.pdfX.size() != n + 1 || img.cdfX.size() != n + 1 ||
+            img.pdfY.size() != (size_t)img.probeH + 1 || img.cdfY.size() != (size_t)img.probeH + 1)
+            return *why = "probe tables do not match the probe size", false;
     }
     return true;
 }
@@ -1027,6 +1207,8 @@ static bool validate_scene(const tb200_scene* s, std::string* why)
     return true;
 }
 
+static tb200_renderer* create_with(int device, const std::function<bool(tb200_renderer*)>& build);
+
 tb200_renderer* tb200_create(const tb200_scene* scene, int device)
 {
     g_error.clear();
@@ -1041,6 +1223,51 @@ tb200_renderer* tb200_create(const tb200_scene* scene, int device)
             return nullptr;
         }
     }
+    return create_with(device, [scene](tb200_renderer* r) { return build_scene(r, scene); });
+}
+
+int tb200_scene_cache_save(const tb200_scene* scene, const char* path)
+{
+    g_error.clear();
+    if (!scene || !path) {
+        set_error("tb200_scene_cache_save: null argument");
+        return -1;
+    }
+    std::string why;
+    if (!validate_scene(scene, &why)) {
+        set_error("tb200_scene_cache_save: invalid scene: " + why);
+        return -1;
+    }
+    SceneImage img;
+    if (!image_from_scene(scene, &img)) return -1;
+    return image_save(img, path) ? 0 : -1;
+}
+
+tb200_renderer* tb200_create_cached(const char* path, int device)
+{
+    g_error.clear();
+    if (!path) {
+        set_error("tb200_create_cached: null path");
+        return nullptr;
+    }
+    // SceneImage is heavy (hundreds of MB for a big mesh + probe): shared with the build step, freed after it
+    std::shared_ptr<SceneImage> img(new SceneImage());
+    try {
+        if (!image_load(path, img.get())) return nullptr;
+    } catch (const std::exception& e) {   // bad_alloc from a corrupt count that passed the size check
+        set_error(std::string("tb200_create_cached: ") + e.what());
+        return nullptr;
+    }
+    std::string why;
+    if (!validate_image(*img, &why)) {
+        set_error("tb200_create_cached: invalid cache file: " + why);
+        return nullptr;
+    }
+    return create_with(device, [img](tb200_renderer* r) { return upload_image(r, *img); });
+}
+
+static tb200_renderer* create_with(int device, const std::function<bool(tb200_renderer*)>& build)
+{
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
         cudaGetLastError();
@@ -1083,7 +1310,7 @@ tb200_renderer* tb200_create(const tb200_scene* scene, int device)
     }
     memset(hostFlags, 0, TB_MAX_BANDS * sizeof(unsigned int));
     r->hBandFlags = hostFlags;
-    if (!build_scene(r, scene)) {
+    if (!build(r)) {
         tb200_destroy(r);
         return nullptr;
     }

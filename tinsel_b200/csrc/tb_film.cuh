@@ -45,10 +45,15 @@ TB_DEV float filter_gaussian(const DFilm& f, float x)
     return tb_max(0.0f, tb_expf(arg) - f.filterOffset);
 }
 
-// one 16-byte vector reduction per touched pixel (sm_90+: red.global.add.v4.f32)
+// one 16-byte vector REDUCTION per touched pixel: red.global.add.v4.f32 (REDG.E.ADD.F32x4).  CUDA's
+// atomicAdd(float4*) compiles to the value-returning form (ATOMG), which makes the warp wait a round trip
+// to L2 for a result nobody reads; the reduction is fire-and-forget.  Same adder, same rounding.  (The L2
+// vector adder flushes denormal sums to zero -- ".FTZ" in the SASS mnemonic -- where the CPU's `+=` keeps
+// them: the one place this renderer is not IEEE-exact; irrelevant at the 1e-4 image tolerance, and
+// per-sample radiance never passes through it.)
 TB_DEV void accum_add(float4* accum, int idx, float r, float g, float b, float w)
 {
-    atomicAdd(&accum[idx], make_float4(r, g, b, w));
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(accum + idx), "f"(r), "f"(g), "f"(b), "f"(w) : "memory");
 }
 
 // CpuRenderer::AddSample, render.cpp:401-445.  Pixels whose weight is exactly zero are skipped

@@ -97,6 +97,14 @@ struct Wf2Shared {
     ProgOp flat[32];
 };
 
+// dynamic shared memory of a CTA: the slot arrays; a build with fewer slots (experiments) still claims
+// a whole SM, so that the slot count per SM is what changes
+#ifdef TB_WF2_PAD_SMEM
+#define TB_WF2_SMEM_BYTES (sizeof(Wf2Shared) > 204000 ? sizeof(Wf2Shared) : (size_t)204000)
+#else
+#define TB_WF2_SMEM_BYTES sizeof(Wf2Shared)
+#endif
+
 // stage queues.  T, A, B, R in the cyclic order of the free-running sweep; F0/F1 hold the freshly
 // regenerated camera rays in hard-phase mode (double-buffered: R fills one while T drains the other)
 // TM (free-running mode, scenes with DScene::splitValid): rays that enter the big mesh's box; same
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     const int tid = threadIdx.x;
     constexpr bool offload = MODE == WF2_MODE_OFFLOAD;
     if (offload && (int)blockIdx.x >= P.walk.numShaders) {
-        wf2_walker_role<THREADS>(P, wf_smem_raw, (int)sizeof(Wf2Shared));
+        wf2_walker_role<THREADS>(P, wf_smem_raw, (int)TB_WF2_SMEM_BYTES);
         return;
     }
 
@@ -486,6 +494,11 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
 
     const int maxDepth = P.film.maxDepth;
     const int lane = tid & 31;
+#ifdef WALK_SHADER_WARPS
+    // offload mode: with most slots parked at the walkers, fewer warps per shader CTA keep fuller chunks and
+    // fewer distinct stages in flight (experiment knob)
+    if (offload && (tid >> 5) >= WALK_SHADER_WARPS) return;
+#endif
 
     // Two scheduling modes share the stage code below (P.hardPhases, uniform for the launch):
     //
@@ -872,8 +885,8 @@ static int wavefront2_ctas_per_sm()
     std::lock_guard<std::mutex> guard(lock);
     if (ctasPerSM[dev] == 0) {
         int n = 0;
-        cudaFuncSetAttribute(k_wavefront2<THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wf2Shared));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront2<THREADS, MODE>, THREADS, sizeof(Wf2Shared)) != cudaSuccess || n < 1)
+        cudaFuncSetAttribute(k_wavefront2<THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_WF2_SMEM_BYTES);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront2<THREADS, MODE>, THREADS, TB_WF2_SMEM_BYTES) != cudaSuccess || n < 1)
             n = 1;
         ctasPerSM[dev] = n;
     }
@@ -895,12 +908,12 @@ static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t 
         if (want < (unsigned long long)shaders) shaders = (int)std::max<unsigned long long>(1ull, want);
         q.walk.numShaders = shaders;
         q.walk.numWalkers = walkers;
-        k_wavefront2<THREADS, MODE><<<shaders + walkers, THREADS, sizeof(Wf2Shared), stream>>>(q, total);
+        k_wavefront2<THREADS, MODE><<<shaders + walkers, THREADS, TB_WF2_SMEM_BYTES, stream>>>(q, total);
         return;
     }
     if (want < (unsigned long long)grid) grid = (int)want;
     if (grid < 1) grid = 1;
-    k_wavefront2<THREADS, MODE><<<grid, THREADS, sizeof(Wf2Shared), stream>>>(p, total);
+    k_wavefront2<THREADS, MODE><<<grid, THREADS, TB_WF2_SMEM_BYTES, stream>>>(p, total);
 }
 
 void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
