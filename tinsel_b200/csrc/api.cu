@@ -307,6 +307,7 @@ struct tb200_renderer {
     float* dRadiance = nullptr;   // tb200_trace_frame scratch
     float* dRaster = nullptr;
     unsigned long long* dCounter = nullptr;
+    float4* dCold = nullptr;      // cold half of the wavefront's slot state (wavefront2.cuh): 128 B per slot
     int frame = 0;
 
     // display/finish step (tb200_finish)
@@ -381,6 +382,8 @@ void free_device(tb200_renderer* r)
     cudaFree(r->dRaster);
     cudaFree(r->dCounter);
     r->dCounter = nullptr;
+    cudaFree(r->dCold);
+    r->dCold = nullptr;
     cudaFree(r->dBandCount);
     r->dBandCount = nullptr;
     cudaFree(r->dWalkBlock);
@@ -875,6 +878,7 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     }
     P->accum = r->boundAccum ? r->boundAccum : r->dAccum;
     P->sampleCounter = r->dCounter;
+    P->cold = r->dCold;
     P->hardPhases = r->hardPhases;
     P->wideCta = r->wideCta;
     P->firstRow = 0;
@@ -1298,7 +1302,9 @@ static tb200_renderer* create_with(int device, const std::function<bool(tb200_re
     const char* rb = getenv("TINSEL_B200_READBACK");
     if (rb && strcmp(rb, "plain") == 0) r->streamedReadback = 0;
     unsigned int* hostFlags = nullptr;
-    if (cudaMalloc((void**)&r->dCounter, sizeof(unsigned long long)) != cudaSuccess ||
+    // cold slot state for every CTA a launch can have (one or two per SM, see launch_wavefront2)
+    if (cudaMalloc((void**)&r->dCold, size_t(r->numSMs) * TB_WF2_MAX_CTAS_PER_SM * TB_WF2_SLOTS * 128) != cudaSuccess ||
+        cudaMalloc((void**)&r->dCounter, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc((void**)&r->dBandCount, TB_MAX_BANDS * sizeof(unsigned int)) != cudaSuccess ||
         cudaHostAlloc((void**)&hostFlags, TB_MAX_BANDS * sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&r->dBandFlags, hostFlags, 0) != cudaSuccess ||

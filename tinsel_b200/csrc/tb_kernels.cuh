@@ -5,10 +5,10 @@
 
 // Mesh-walk offload of the wavefront kernel (wavefront_walk.cuh): the queues between shader CTAs and
 // walker CTAs, in global memory.  numWalkers == 0: the launch does not use it.
-#ifndef TB_WF2_PATHS
-#define TB_WF2_PATHS 1024   // path slots per CTA of the wavefront kernel: a power of two <= 1024 (10-bit slot ids in the queue cells)
-#endif
-#define TB_WF2_SLOTS TB_WF2_PATHS
+// path slots per CTA of the wavefront kernel, at most (the layouts of kernels.cu use 1024 and 2048): the host
+// sizes the cold slot state and the offload queues with it
+#define TB_WF2_SLOTS 2048
+#define TB_WF2_MAX_CTAS_PER_SM 2   // the launch never places more CTAs per SM (the host sizes the cold state with it)
 struct WalkParams {
     uint4* reqRing;                // (1 << reqLog2) cells x 3 chunks of 16 bytes
     unsigned int reqLog2;
@@ -52,6 +52,8 @@ struct LaunchParams {
     unsigned int bandSamples;
     unsigned int bandTag;
     WalkParams walk;
+    // cold half of the wavefront's slot state: 8 x float4 per slot, TB_WF2_PATHS slots per CTA of the launch
+    float4* cold;
 };
 
 #define TB_MAX_BANDS 64

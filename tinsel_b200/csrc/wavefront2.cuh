@@ -31,10 +31,13 @@
 // instruction cache: 32 KB of L1.5 against ~150 KB of kernel); block-synchronous hard phases with
 // ticket claims for scenes where every hit spawns several shadow rays; and free-running with a
 // second trace queue for rays that enter a big mesh.
-#pragma once
-
-#include <algorithm>
-#include <mutex>
+//
+// This header is compiled TWICE by kernels.cu, in two namespaces, for the two layouts of the slot state
+// (chosen with TB_WF2_PATHS / TB_WF2_COLD_SMEM before each inclusion; see kernels.cu):
+//   wf2_smem  1024 slots per CTA, the whole state in shared memory -- scenes held on chip, 512-thread CTAs
+//   wf2_l2    2048 slots per CTA, the cold half of the state in global memory (L2) -- scenes with deep
+//             mesh BVHs (768-thread CTAs, and the offload mode), which gain from more paths in flight
+// so it has no include guard, and only defines macros whose text is the same both times.
 
 #ifndef TB_WF2_THREADS
 #define TB_WF2_THREADS 512
@@ -45,40 +48,53 @@
 #ifndef TB_WF2_CTAS_PER_SM
 #define TB_WF2_CTAS_PER_SM 1
 #endif
-static_assert(TB_WF2_PATHS == TB_WF2_SLOTS, "the host sizes the offload queues with TB_WF2_SLOTS");
+static_assert(TB_WF2_PATHS <= TB_WF2_SLOTS, "the host sizes the cold slot state and the offload queues with TB_WF2_SLOTS");
 #define TB_WF2_MAX_PRIMS 16     // scene tables up to this size are staged in shared memory
 #define TB_WF2_MAX_PAIRS 16
 
 enum { WF2_PH_EXT = 0, WF2_PH_NEE = 1 };
+#define WF2_FLAG_EMPTY 1u   // the slot holds no sample (before its first camera ray)
+
+// Cold half of a slot's state: eight 16-byte chunks (seven used) per slot in global memory, read with
+// ld.global.cg / written with st.global.cg by the one lane that owns the slot at the time (ownership
+// moves through the stage queues, whose pushes are preceded by a block-scope fence).
+//   0: T.xyz, eta        1: L.xyz, bsdfPdf     2: absorption.xyz, sample index
+//   3: rng1, rng2, NEE cursor, sampled light   4: shadow dist, light normal.xyz
+//   5: sky pdf, NEE sum.xyz                     6: NEE radiance accumulator.xyz
+// TB_WF2_COLD_SMEM: the same records in SHARED memory instead (stride 7 chunks), for builds with few enough
+// slots per CTA: the cold half then costs 7 128-bit accesses per stage instead of 27 32-bit ones.
+#ifdef TB_WF2_COLD_SMEM
+enum { CC_T = 0, CC_L = 1, CC_A = 2, CC_RNG = 3, CC_SH = 4, CC_SUM = 5, CC_LA = 6, CC_CHUNKS = 7 };
+TB_DEV float4 cold_ld(const float4* rec, int c) { return rec[c]; }
+TB_DEV void cold_st(float4* rec, int c, float x, float y, float z, float w) { rec[c] = make_float4(x, y, z, w); }
+#else
+enum { CC_T = 0, CC_L = 1, CC_A = 2, CC_RNG = 3, CC_SH = 4, CC_SUM = 5, CC_LA = 6, CC_CHUNKS = 8 };
+TB_DEV float4 cold_ld(const float4* rec, int c) { return __ldcg(rec + c); }
+TB_DEV void cold_st(float4* rec, int c, float x, float y, float z, float w) { __stcg(rec + c, make_float4(x, y, z, w)); }
+#endif
+TB_DEV float u2f(uint32_t v) { return __uint_as_float(v); }
+TB_DEV uint32_t f2u(float v) { return __float_as_uint(v); }
 
 struct Wf2Shared {
-    // path state
+    // HOT half of the slot state: what stage T (trace) reads and writes for every ray.  The cold half --
+    // throughput, radiance, medium, RNG, the NEE bookkeeping: 27 words that only stages R, A and B touch,
+    // once per ray -- lives in a 128-byte record per slot in global memory (Wf2Cold, L2-resident).  The
+    // wavefront is bound by the number of paths an SM has in flight (halving the slots halves the
+    // throughput on every scene, profiles/README.md round 2), and 18 words instead of 45 per slot double it.
     float ox[TB_WF2_PATHS], oy[TB_WF2_PATHS], oz[TB_WF2_PATHS];
     float dx[TB_WF2_PATHS], dy[TB_WF2_PATHS], dz[TB_WF2_PATHS];
     float time[TB_WF2_PATHS];
-    float Tx[TB_WF2_PATHS], Ty[TB_WF2_PATHS], Tz[TB_WF2_PATHS];
-    float Lx[TB_WF2_PATHS], Ly[TB_WF2_PATHS], Lz[TB_WF2_PATHS];
-    float eta[TB_WF2_PATHS];
-    float ax[TB_WF2_PATHS], ay[TB_WF2_PATHS], az[TB_WF2_PATHS];
-    float bsdfPdf[TB_WF2_PATHS];
-    uint32_t rng1[TB_WF2_PATHS], rng2[TB_WF2_PATHS];
-    uint32_t sample[TB_WF2_PATHS];    // sample index within the launch
-    uint32_t flags[TB_WF2_PATHS];     // bits 1-2 rayType, bit 3 phase, bits 8.. bounce
+    uint32_t flags[TB_WF2_PATHS];     // bit 0 empty (no sample yet), bits 1-2 rayType, bit 3 phase, bits 8.. bounce
     // extension-ray hit
     float ht[TB_WF2_PATHS], hnx[TB_WF2_PATHS], hny[TB_WF2_PATHS], hnz[TB_WF2_PATHS];
     int hprim[TB_WF2_PATHS];
     // pending shadow ray (origin is recomputed from the surface point) and its result
     float sdx[TB_WF2_PATHS], sdy[TB_WF2_PATHS], sdz[TB_WF2_PATHS];
-    float sdist[TB_WF2_PATHS];
-    float slx[TB_WF2_PATHS], sly[TB_WF2_PATHS], slz[TB_WF2_PATHS];
-    float spdf[TB_WF2_PATHS];
-    int slight[TB_WF2_PATHS];
     float st[TB_WF2_PATHS];
     int sprim[TB_WF2_PATHS];
-    // NEE cursor
-    float sumx[TB_WF2_PATHS], sumy[TB_WF2_PATHS], sumz[TB_WF2_PATHS];
-    float lax[TB_WF2_PATHS], lay[TB_WF2_PATHS], laz[TB_WF2_PATHS];
-    uint32_t cursor[TB_WF2_PATHS];    // slot | prim << 8 | sample << 20
+#ifdef TB_WF2_COLD_SMEM
+    float4 cold[TB_WF2_PATHS * 7];
+#endif
     // stage queues: rings of lap-tagged slot ids
     uint16_t ring[7][TB_WF2_PATHS];
     unsigned int head[7], tail[7];
@@ -112,14 +128,17 @@ struct Wf2Shared {
 // from T with none.
 enum { WF2_Q_T = 0, WF2_Q_A = 1, WF2_Q_B = 2, WF2_Q_R = 3, WF2_Q_F0 = 4, WF2_Q_F1 = 5, WF2_Q_TM = 6 };
 #define WF2_MASK (TB_WF2_PATHS - 1)
-#define WF2_LOG2_PATHS (TB_WF2_PATHS == 1024 ? 10 : TB_WF2_PATHS == 512 ? 9 : TB_WF2_PATHS == 256 ? 8 : 7)
+#define WF2_LOG2_PATHS (TB_WF2_PATHS == 2048 ? 11 : TB_WF2_PATHS == 1024 ? 10 : TB_WF2_PATHS == 512 ? 9 : TB_WF2_PATHS == 256 ? 8 : 7)
+#define WF2_SLOT_BITS 11                      // queue cells: slot id in the low 11 bits, lap tag (1..31) above
+#define WF2_SLOT_MASK ((1u << WF2_SLOT_BITS) - 1u)
+static_assert(TB_WF2_PATHS <= (1 << WF2_SLOT_BITS) && (TB_WF2_PATHS & (TB_WF2_PATHS - 1)) == 0, "slot ids must fit the queue cells");
 
-// cell value of ring index i holding slot s: the lap tag (1..63, never 0) makes "reserved but not
+// cell value of ring index i holding slot s: the lap tag (1..31, never 0) makes "reserved but not
 // yet written" and "left over from the previous lap" distinguishable from the expected entry
 TB_DEV uint16_t wf2_cell(unsigned int index, int slot)
 {
-    const unsigned int lap = ((index >> WF2_LOG2_PATHS) % 63u) + 1u;
-    return (uint16_t)((unsigned)slot | (lap << 10));
+    const unsigned int lap = ((index >> WF2_LOG2_PATHS) % 31u) + 1u;
+    return (uint16_t)((unsigned)slot | (lap << WF2_SLOT_BITS));
 }
 
 // append `slot` to stage queue q for every lane with flag == true: ballot + prefix sum, one shared
@@ -188,7 +207,7 @@ TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot)
         // optimistic read; entries reserved by a producer but not yet stored end the chunk early
         const unsigned int idx = h + (unsigned)lane;
         const uint16_t cell = *(volatile uint16_t*)&S.ring[q][idx & WF2_MASK];
-        const bool ok = lane < n && (cell >> 10) == (((idx >> WF2_LOG2_PATHS) % 63u) + 1u);
+        const bool ok = lane < n && (unsigned)(cell >> WF2_SLOT_BITS) == (((idx >> WF2_LOG2_PATHS) % 31u) + 1u);
         const unsigned good = __ballot_sync(0xffffffffu, ok);
         n = (good == 0xffffffffu) ? 32 : __ffs(~good) - 1;   // length of the valid prefix
         if (n <= 0) {
@@ -200,7 +219,7 @@ TB_DEV int wf2_claim(Wf2Shared& S, int q, int minCount, int& slot)
         got = __shfl_sync(0xffffffffu, got, 0);
         if (got == h) {
             __threadfence_block();   // the producer's state writes precede its cell store
-            slot = (int)(cell & 1023u);
+            slot = (int)(cell & WF2_SLOT_MASK);
             return n;
         }
         // lost the race to another warp, which made progress: try again
@@ -219,11 +238,11 @@ TB_DEV int wf2_claim_ticket(Wf2Shared& S, int q, unsigned int tail, int& slot)
     const int avail = (int)(tail - base);
     if (avail <= 0) return 0;
     const int n = avail < 32 ? avail : 32;
-    if (lane < n) slot = (int)(*(volatile uint16_t*)&S.ring[q][(base + (unsigned)lane) & WF2_MASK] & 1023u);
+    if (lane < n) slot = (int)(*(volatile uint16_t*)&S.ring[q][(base + (unsigned)lane) & WF2_MASK] & WF2_SLOT_MASK);
     return n;
 }
 
-TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s)
+TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s, float eta)
 {
     // the quantities path_hit() derives from the path and the hit record (render.cpp:255-278)
     Surface sf;
@@ -233,7 +252,7 @@ TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s)
     sf.p = o + d * S.ht[s];
     sf.n = v3(S.hnx[s], S.hny[s], S.hnz[s]);
     sf.wo = -d;
-    sf.etaI = S.eta[s];
+    sf.etaI = eta;
     const DPrim& prim = sc.prims[sf.prim];
     if (sf.etaI == 1.0f) {
         sf.etaO = prim.mat.ior;
@@ -277,22 +296,21 @@ static __device__ __noinline__ void wf2_band_pad(unsigned int* bandCount, volati
     }
 }
 
-TB_DEV void wf2_store_shadow(Wf2Shared& S, int s, const ShadowRay& sr, const NeeCursor& c)
+// the pending shadow ray and the NEE bookkeeping that waits for its result
+TB_DEV void wf2_store_shadow(Wf2Shared& S, float4* rec, int s, const ShadowRay& sr, const NeeCursor& c, Rng rng)
 {
     S.sdx[s] = sr.d.x; S.sdy[s] = sr.d.y; S.sdz[s] = sr.d.z;
-    S.sdist[s] = sr.dist;
-    S.slx[s] = sr.lightN.x; S.sly[s] = sr.lightN.y; S.slz[s] = sr.lightN.z;
-    S.spdf[s] = sr.skyPdf;
-    S.slight[s] = sr.light;
-    S.sumx[s] = c.sum.x; S.sumy[s] = c.sum.y; S.sumz[s] = c.sum.z;
-    S.lax[s] = c.Lacc.x; S.lay[s] = c.Lacc.y; S.laz[s] = c.Lacc.z;
-    S.cursor[s] = (uint32_t)c.slot | ((uint32_t)c.prim << 8) | ((uint32_t)c.sample << 20);
+    const uint32_t cursor = (uint32_t)c.slot | ((uint32_t)c.prim << 8) | ((uint32_t)c.sample << 20);
+    cold_st(rec, CC_RNG, u2f(rng.s1), u2f(rng.s2), u2f(cursor), __int_as_float(sr.light));
+    cold_st(rec, CC_SH, sr.dist, sr.lightN.x, sr.lightN.y, sr.lightN.z);
+    cold_st(rec, CC_SUM, sr.skyPdf, c.sum.x, c.sum.y, c.sum.z);
+    cold_st(rec, CC_LA, c.Lacc.x, c.Lacc.y, c.Lacc.z, 0.0f);
 }
 
 // finish the shading of a surface hit once all NEE samples are folded: BSDF sample, next ray
 // (path_scatter) or termination.  Returns true when the slot continues with a new extension ray.
-TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf, V3 T, V3 L, Rng rng, float time, V3 neeSum,
-                        int bounce, int maxDepth)
+TB_DEV bool wf2_scatter(Wf2Shared& S, float4* rec, const DScene& sc, int s, const Surface& sf, V3 T, V3 L, Rng rng, float time, V3 neeSum,
+                        int bounce, int maxDepth, V3 absorb, float bsdfPdf, uint32_t sample)
 {
     PathState ps;
     ps.o = v3s(0.0f);
@@ -301,9 +319,9 @@ TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf
     ps.T = T;
     ps.L = L;
     ps.eta = sf.etaI;
-    ps.absorb = v3(S.ax[s], S.ay[s], S.az[s]);
+    ps.absorb = absorb;
     ps.rayType = (int)((S.flags[s] >> 1) & 3u);
-    ps.bsdfPdf = S.bsdfPdf[s];
+    ps.bsdfPdf = bsdfPdf;
     ps.rng = rng;
     bool go;
     if (bounce + 1 >= maxDepth) {
@@ -313,16 +331,13 @@ TB_DEV bool wf2_scatter(Wf2Shared& S, const DScene& sc, int s, const Surface& sf
     } else {
         go = path_scatter(sc, ps, sf, neeSum);
     }
-    S.Lx[s] = ps.L.x; S.Ly[s] = ps.L.y; S.Lz[s] = ps.L.z;
+    cold_st(rec, CC_L, ps.L.x, ps.L.y, ps.L.z, ps.bsdfPdf);
     if (!go) return false;
     S.ox[s] = ps.o.x; S.oy[s] = ps.o.y; S.oz[s] = ps.o.z;
     S.dx[s] = ps.d.x; S.dy[s] = ps.d.y; S.dz[s] = ps.d.z;
-    S.Tx[s] = ps.T.x; S.Ty[s] = ps.T.y; S.Tz[s] = ps.T.z;
-    S.eta[s] = ps.eta;
-    S.ax[s] = ps.absorb.x; S.ay[s] = ps.absorb.y; S.az[s] = ps.absorb.z;
-    S.bsdfPdf[s] = ps.bsdfPdf;
-    S.rng1[s] = ps.rng.s1;
-    S.rng2[s] = ps.rng.s2;
+    cold_st(rec, CC_T, ps.T.x, ps.T.y, ps.T.z, ps.eta);
+    cold_st(rec, CC_A, ps.absorb.x, ps.absorb.y, ps.absorb.z, u2f(sample));
+    cold_st(rec, CC_RNG, u2f(ps.rng.s1), u2f(ps.rng.s2), 0.0f, 0.0f);
     S.flags[s] = ((uint32_t)ps.rayType << 1) | ((uint32_t)WF2_PH_EXT << 3) | ((uint32_t)(bounce + 1) << 8);
     return true;
 }
@@ -367,8 +382,8 @@ TB_DEV int wf2_claim_answers(Wf2Shared& S, const WalkParams& W, int kind, int mi
 TB_DEV void wf2_merge_answer(Wf2Shared& S, const DScene& sc, int s, bool isExt, uint4 c0, uint4 c1, uint4 c2)
 {
     const uint32_t info = c2.z;
-    const bool hit = ((info >> 18) & 1u) != 0u, tie = ((info >> 19) & 1u) != 0u;
-    const int primM = (int)((info >> 10) & 0xffu);
+    const bool hit = ((info >> (WF2_SLOT_BITS + 8)) & 1u) != 0u, tie = ((info >> (WF2_SLOT_BITS + 9)) & 1u) != 0u;
+    const int primM = (int)((info >> WF2_SLOT_BITS) & 0xffu);
     const float tM = __uint_as_float(c0.x);
     const float partialT = isExt ? S.ht[s] : S.st[s];
     const int partialPrim = isExt ? S.hprim[s] : S.sprim[s];
@@ -472,7 +487,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
         S.ring[WF2_Q_F0][s] = 0;
         S.ring[WF2_Q_F1][s] = 0;
         S.ring[WF2_Q_TM][s] = 0;
-        S.sample[s] = 0xffffffffu;
+        S.flags[s] = WF2_FLAG_EMPTY;
     }
     if (tid == 0) {
         for (int q = 0; q < 7; ++q) S.head[q] = S.tail[q] = 0u;
@@ -494,6 +509,11 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
 
     const int maxDepth = P.film.maxDepth;
     const int lane = tid & 31;
+#ifdef TB_WF2_COLD_SMEM
+    float4* const coldBase = S.cold;
+#else
+    float4* const coldBase = P.cold + (size_t)blockIdx.x * TB_WF2_PATHS * CC_CHUNKS;
+#endif
 #ifdef WALK_SHADER_WARPS
     // offload mode: with most slots parked at the walkers, fewer warps per shader CTA keep fuller chunks and
     // fewer distinct stages in flight (experiment knob)
@@ -581,7 +601,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                         if (n > 0) {
                             stage = pos == 1 ? WF2_Q_A : WF2_Q_B;
                             fromAnswer = true;
-                            s = (int)(ans2.z & 1023u);
+                            s = (int)(ans2.z & WF2_SLOT_MASK);
                         }
                     } else {
                         const int q = pos == 0 ? WF2_Q_T : pos == 2 ? WF2_Q_A : pos == 4 ? WF2_Q_B : WF2_Q_R;
@@ -633,21 +653,25 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
 
         if (stage == WF2_Q_R) {
             // ===================== R: splat the finished sample, regenerate =======================
-            if (active && S.sample[s] != 0xffffffffu) {
+            float4* rec = coldBase + (size_t)s * CC_CHUNKS;
+            const bool finished = active && !(S.flags[s] & WF2_FLAG_EMPTY);
+            uint32_t doneSample = 0xffffffffu;
+            if (finished) {
+                const float4 cl = cold_ld(rec, CC_L), ca = cold_ld(rec, CC_A);
+                doneSample = f2u(ca.w);
                 int px, py, frame;
-                decode_sample(P, (unsigned long long)S.sample[s], px, py, frame);
+                decode_sample(P, (unsigned long long)doneSample, px, py, frame);
                 // raster position of the sample: its first two RNG draws (render.cpp:476,481-482)
                 Rng rr = rng_seed(tb_sample_seed((uint32_t)(py * P.film.width + px), (uint32_t)frame));
                 float rx = rng_float(rr);
                 float ry = rng_float(rr);
                 rx += px;
                 ry += py;
-                sample_end(P, px, py, rx, ry, v3(S.Lx[s], S.Ly[s], S.Lz[s]));
+                sample_end(P, px, py, rx, ry, v3(cl.x, cl.y, cl.z));
             }
             if (P.bandFlags)
-                wf2_band_report(P.bandCount, P.bandFlags, P.bandSamples, (uint32_t)P.samplesPerFrame, P.bandTag, S.sample[s],
-                                active && S.sample[s] != 0xffffffffu);
-            if (active) S.sample[s] = 0xffffffffu;
+                wf2_band_report(P.bandCount, P.bandFlags, P.bandSamples, (uint32_t)P.samplesPerFrame, P.bandTag, doneSample, finished);
+            if (active) S.flags[s] = WF2_FLAG_EMPTY;
             // claim a new sample; indices on tile padding outside the image are skipped
             bool want = active && !*(volatile int*)&S.exhausted;
             bool fresh = false;
@@ -674,14 +698,10 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                             S.ox[s] = ps.o.x; S.oy[s] = ps.o.y; S.oz[s] = ps.o.z;
                             S.dx[s] = ps.d.x; S.dy[s] = ps.d.y; S.dz[s] = ps.d.z;
                             S.time[s] = ps.time;
-                            S.Tx[s] = 1.0f; S.Ty[s] = 1.0f; S.Tz[s] = 1.0f;
-                            S.Lx[s] = 0.0f; S.Ly[s] = 0.0f; S.Lz[s] = 0.0f;
-                            S.eta[s] = 1.0f;
-                            S.ax[s] = 0.0f; S.ay[s] = 0.0f; S.az[s] = 0.0f;
-                            S.bsdfPdf[s] = 1.0f;
-                            S.rng1[s] = ps.rng.s1;
-                            S.rng2[s] = ps.rng.s2;
-                            S.sample[s] = (uint32_t)idx;
+                            cold_st(rec, CC_T, 1.0f, 1.0f, 1.0f, 1.0f);                     // throughput 1, eta 1
+                            cold_st(rec, CC_L, 0.0f, 0.0f, 0.0f, 1.0f);                     // radiance 0, bsdfPdf 1
+                            cold_st(rec, CC_A, 0.0f, 0.0f, 0.0f, u2f((uint32_t)idx));      // no absorption, the sample index
+                            cold_st(rec, CC_RNG, u2f(ps.rng.s1), u2f(ps.rng.s2), 0.0f, 0.0f);
                             S.flags[s] = ((uint32_t)TB_REFLECTED << 1) | ((uint32_t)WF2_PH_EXT << 3);
                             fresh = true;
                             want = false;
@@ -747,7 +767,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                     if (pn) atomicAdd(&S.ansPending[WALK_KIND_SHADOW], __popc(pn));
                 }
                 walk_post(P.walk, park, postO, postD, postTime, parkMask,
-                          (uint32_t)s | ((isExt ? WALK_KIND_EXT : WALK_KIND_SHADOW) << 10) | ((uint32_t)blockIdx.x << 11));
+                          (uint32_t)s | ((isExt ? WALK_KIND_EXT : WALK_KIND_SHADOW) << WF2_SLOT_BITS) | ((uint32_t)blockIdx.x << (WF2_SLOT_BITS + 1)));
                 isExt = isExt && !park;
                 isNee = isNee && !park;
             }
@@ -758,6 +778,8 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             bool cont = false, fin = false;
             if (offload && fromAnswer && active) wf2_merge_answer(S, sc, s, true, ans0, ans1, ans2);
             if (active) {
+                float4* rec = coldBase + (size_t)s * CC_CHUNKS;
+                const float4 ct = cold_ld(rec, CC_T), cl = cold_ld(rec, CC_L);
                 const uint32_t fl = S.flags[s];
                 const int bounce = (int)(fl >> 8);
                 const int hprim = S.hprim[s];
@@ -765,28 +787,29 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                     if (hprim == -1) {
                         PathState ps;
                         ps.d = v3(S.dx[s], S.dy[s], S.dz[s]);
-                        ps.T = v3(S.Tx[s], S.Ty[s], S.Tz[s]);
-                        ps.L = v3(S.Lx[s], S.Ly[s], S.Lz[s]);
+                        ps.T = v3(ct.x, ct.y, ct.z);
+                        ps.L = v3(cl.x, cl.y, cl.z);
                         ps.rayType = (int)((fl >> 1) & 3u);
-                        ps.bsdfPdf = S.bsdfPdf[s];
+                        ps.bsdfPdf = cl.w;
                         path_miss(sc, ps, bounce);
-                        S.Lx[s] = ps.L.x; S.Ly[s] = ps.L.y; S.Lz[s] = ps.L.z;
+                        cold_st(rec, CC_L, ps.L.x, ps.L.y, ps.L.z, cl.w);
                     }
                     fin = true;
                 } else {
                     // hit prologue (render.cpp:255-310)
+                    const float4 ca = cold_ld(rec, CC_A), cr = cold_ld(rec, CC_RNG);
                     PathState ps;
                     ps.o = v3(S.ox[s], S.oy[s], S.oz[s]);
                     ps.d = v3(S.dx[s], S.dy[s], S.dz[s]);
                     ps.time = S.time[s];
-                    ps.T = v3(S.Tx[s], S.Ty[s], S.Tz[s]);
-                    ps.L = v3(S.Lx[s], S.Ly[s], S.Lz[s]);
-                    ps.eta = S.eta[s];
-                    ps.absorb = v3(S.ax[s], S.ay[s], S.az[s]);
+                    ps.T = v3(ct.x, ct.y, ct.z);
+                    ps.L = v3(cl.x, cl.y, cl.z);
+                    ps.eta = ct.w;
+                    ps.absorb = v3(ca.x, ca.y, ca.z);
                     ps.rayType = (int)((fl >> 1) & 3u);
-                    ps.bsdfPdf = S.bsdfPdf[s];
-                    ps.rng.s1 = S.rng1[s];
-                    ps.rng.s2 = S.rng2[s];
+                    ps.bsdfPdf = cl.w;
+                    ps.rng.s1 = f2u(cr.x);
+                    ps.rng.s2 = f2u(cr.y);
                     Hit h;
                     h.t = S.ht[s];
                     h.n = v3(S.hnx[s], S.hny[s], S.hnz[s]);
@@ -797,16 +820,14 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                     nee_begin(c);
                     ShadowRay sr;
                     if (nee_generate(sc, sf, ps.time, c, ps.rng, sr)) {
-                        S.Tx[s] = ps.T.x; S.Ty[s] = ps.T.y; S.Tz[s] = ps.T.z;
-                        S.Lx[s] = ps.L.x; S.Ly[s] = ps.L.y; S.Lz[s] = ps.L.z;
-                        S.rng1[s] = ps.rng.s1;
-                        S.rng2[s] = ps.rng.s2;
-                        wf2_store_shadow(S, s, sr, c);
+                        cold_st(rec, CC_T, ps.T.x, ps.T.y, ps.T.z, ct.w);
+                        cold_st(rec, CC_L, ps.L.x, ps.L.y, ps.L.z, cl.w);
+                        wf2_store_shadow(S, rec, s, sr, c, ps.rng);
                         S.flags[s] = (fl & ~(1u << 3)) | ((uint32_t)WF2_PH_NEE << 3);
                         cont = true;
                     } else {
                         // scene without lights or probe: straight to the BSDF
-                        cont = wf2_scatter(S, sc, s, sf, ps.T, ps.L, ps.rng, ps.time, c.sum, bounce, maxDepth);
+                        cont = wf2_scatter(S, rec, sc, s, sf, ps.T, ps.L, ps.rng, ps.time, c.sum, bounce, maxDepth, ps.absorb, ps.bsdfPdf, f2u(ca.w));
                         fin = !cont;
                     }
                 }
@@ -819,23 +840,26 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             bool cont = false, fin = false;
             if (offload && fromAnswer && active) wf2_merge_answer(S, sc, s, false, ans0, ans1, ans2);
             if (active) {
+                float4* rec = coldBase + (size_t)s * CC_CHUNKS;
+                const float4 ct = cold_ld(rec, CC_T), cl = cold_ld(rec, CC_L), ca = cold_ld(rec, CC_A), cr = cold_ld(rec, CC_RNG);
+                const float4 csh = cold_ld(rec, CC_SH), csum = cold_ld(rec, CC_SUM), cla = cold_ld(rec, CC_LA);
                 const uint32_t fl = S.flags[s];
                 const int bounce = (int)(fl >> 8);
-                const Surface sf = wf2_surface(S, sc, s);
+                const Surface sf = wf2_surface(S, sc, s, ct.w);
                 ShadowRay sr;
                 sr.o = v3s(0.0f);
                 sr.d = v3(S.sdx[s], S.sdy[s], S.sdz[s]);
-                sr.dist = S.sdist[s];
-                sr.lightN = v3(S.slx[s], S.sly[s], S.slz[s]);
-                sr.skyPdf = S.spdf[s];
-                sr.light = S.slight[s];
+                sr.dist = csh.x;
+                sr.lightN = v3(csh.y, csh.z, csh.w);
+                sr.skyPdf = csum.x;
+                sr.light = __float_as_int(cr.w);
                 NeeCursor c;
-                const uint32_t cw = S.cursor[s];
+                const uint32_t cw = f2u(cr.z);
                 c.slot = (int)(cw & 0xffu);
                 c.prim = (int)((cw >> 8) & 0xfffu);
                 c.sample = (int)(cw >> 20);
-                c.sum = v3(S.sumx[s], S.sumy[s], S.sumz[s]);
-                c.Lacc = v3(S.lax[s], S.lay[s], S.laz[s]);
+                c.sum = v3(csum.y, csum.z, csum.w);
+                c.Lacc = v3(cla.x, cla.y, cla.z);
                 Hit sh;
                 sh.t = S.st[s];
                 sh.prim = S.sprim[s];
@@ -843,17 +867,15 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                 nee_connect(sc, sf, sr, sh, c);
 
                 Rng rng;
-                rng.s1 = S.rng1[s];
-                rng.s2 = S.rng2[s];
+                rng.s1 = f2u(cr.x);
+                rng.s2 = f2u(cr.y);
                 const float time = S.time[s];
                 if (nee_generate(sc, sf, time, c, rng, sr)) {
-                    S.rng1[s] = rng.s1;
-                    S.rng2[s] = rng.s2;
-                    wf2_store_shadow(S, s, sr, c);
+                    wf2_store_shadow(S, rec, s, sr, c, rng);
                     cont = true;
                 } else {
-                    cont = wf2_scatter(S, sc, s, sf, v3(S.Tx[s], S.Ty[s], S.Tz[s]), v3(S.Lx[s], S.Ly[s], S.Lz[s]), rng, time, c.sum,
-                                       bounce, maxDepth);
+                    cont = wf2_scatter(S, rec, sc, s, sf, v3(ct.x, ct.y, ct.z), v3(cl.x, cl.y, cl.z), rng, time, c.sum, bounce, maxDepth,
+                                       v3(ca.x, ca.y, ca.z), cl.w, f2u(ca.w));
                     fin = !cont;
                 }
             }
@@ -888,6 +910,7 @@ static int wavefront2_ctas_per_sm()
         cudaFuncSetAttribute(k_wavefront2<THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_WF2_SMEM_BYTES);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront2<THREADS, MODE>, THREADS, TB_WF2_SMEM_BYTES) != cudaSuccess || n < 1)
             n = 1;
+        if (n > TB_WF2_MAX_CTAS_PER_SM) n = TB_WF2_MAX_CTAS_PER_SM;
         ctasPerSM[dev] = n;
     }
     return ctasPerSM[dev];
@@ -916,25 +939,26 @@ static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t 
     k_wavefront2<THREADS, MODE><<<grid, THREADS, TB_WF2_SMEM_BYTES, stream>>>(p, total);
 }
 
-void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
+// the launches of this layout (see the top of the file for which scheduler variants each layout serves)
+void launch_layout(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
 {
     const unsigned long long total = p.samplesPerFrame * (unsigned long long)p.numFrames;
     if (total == 0ull) return;
     cudaMemsetAsync(p.sampleCounter, 0, sizeof(unsigned long long), stream);
     const bool split = !p.hardPhases && p.scene.splitValid;
-    if (p.walk.numWalkers > 0 && !p.hardPhases && p.scene.deferMask != 0u && p.scene.numFlat > 0) {
+#ifdef TB_WF2_COLD_SMEM
+    if (p.hardPhases) launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_HARD>(p, numSMs, stream, total);
+    else if (split) launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_SPLIT>(p, numSMs, stream, total);
+    else launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_GENERIC>(p, numSMs, stream, total);
+#else
+    if (wavefront2_wants_offload(p)) {
         if (p.wideCta) launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_OFFLOAD>(p, numSMs, stream, total);
         else launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_OFFLOAD>(p, numSMs, stream, total);
-        if (launchCount) ++*launchCount;
-        return;
-    }
-    if (p.wideCta) {
-        if (split) launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_SPLIT>(p, numSMs, stream, total);
-        else launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_GENERIC>(p, numSMs, stream, total);
+    } else if (split) {
+        launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_SPLIT>(p, numSMs, stream, total);
     } else {
-        if (p.hardPhases) launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_HARD>(p, numSMs, stream, total);
-        else if (split) launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_SPLIT>(p, numSMs, stream, total);
-        else launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_GENERIC>(p, numSMs, stream, total);
+        launch_wavefront2_t<TB_WF2_THREADS_WIDE, WF2_MODE_GENERIC>(p, numSMs, stream, total);   // hard phases too (run-time flag)
     }
+#endif
     if (launchCount) ++*launchCount;
 }

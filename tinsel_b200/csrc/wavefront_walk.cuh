@@ -32,7 +32,7 @@
 // `t < tmax` culling, strict `t < closestT`), so a mesh's own result is the reference's bit for
 // bit; across primitives the closest hit is order-independent except for exact ties in t, which
 // are detected and redone with the reference-order walk (trace_ordered), as the scene program does.
-#pragma once
+// (no include guard: compiled once per slot-state layout, see wavefront2.cuh)
 
 // second pass of a shader warp's sweep over its work sources takes chunks of at least this many entries
 // (the first pass wants full chunks of 32, a third pass takes anything)
@@ -72,7 +72,7 @@ TB_DEV unsigned int walk_ld1(const unsigned int* p)
 }
 
 // ---- producer side (shader CTAs, stage T) ---------------------------------------------------------
-// `src` = slot | kind << 10 | shader CTA << 11
+// `src` = slot | kind << WF2_SLOT_BITS | shader CTA << (WF2_SLOT_BITS + 1)
 TB_DEV void walk_post(const WalkParams& W, bool flag, V3 o, V3 d, float time, uint32_t primMask, uint32_t src)
 {
     const unsigned m = __ballot_sync(0xffffffffu, flag);
@@ -360,11 +360,12 @@ static __device__ void wf2_walker_role(const LaunchParams& P, unsigned char* sme
                         mh.tri = -1;
                     } else {
                         // the request is finished: answer it
-                        const unsigned int cta = src >> 11, kind = (src >> 10) & 1u, slot = src & 1023u;
+                        const unsigned int cta = src >> (WF2_SLOT_BITS + 1), kind = (src >> WF2_SLOT_BITS) & 1u, slot = src & WF2_SLOT_MASK;
                         const unsigned int idx = atomicAdd(W.ansTail + cta * 2 + kind, 1u);
                         const unsigned int tag = (idx >> WF2_LOG2_PATHS) + 1u;
                         uint4* cell = W.ansRing + ((size_t)(cta * 2 + kind) * TB_WF2_PATHS + (idx & WF2_MASK)) * 3;
-                        const uint32_t info = slot | ((uint32_t)(best.prim & 0xff) << 10) | ((best.prim >= 0 ? 1u : 0u) << 18) | ((tie ? 1u : 0u) << 19);
+                        const uint32_t info = slot | ((uint32_t)(best.prim & 0xff) << WF2_SLOT_BITS) | ((best.prim >= 0 ? 1u : 0u) << (WF2_SLOT_BITS + 8)) |
+                                              ((tie ? 1u : 0u) << (WF2_SLOT_BITS + 9));
                         walk_st(cell + 0, __float_as_uint(best.t), __float_as_uint(best.u), __float_as_uint(best.v), tag);
                         walk_st(cell + 1, __float_as_uint(best.w), __float_as_uint(best.gn.x), __float_as_uint(best.gn.y), tag);
                         walk_st(cell + 2, __float_as_uint(best.gn.z), (uint32_t)best.tri, info, tag);
