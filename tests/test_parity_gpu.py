@@ -223,7 +223,7 @@ def test_both_scheduling_modes_bit_exact(sched, cta):
     offload = sched.startswith("offload")
     os.environ["TINSEL_B200_SCHED"] = "free" if sched == "split" or offload else sched
     os.environ["TINSEL_B200_SPLIT"] = "1" if sched == "split" else "0"
-    os.environ["TINSEL_B200_OFFLOAD"] = "1" if offload else "0"
+    os.environ["TINSEL_B200_OFFLOAD"] = "2" if offload else "0"
     if sched in ("offload1", "offload100"):
         os.environ["TINSEL_B200_WALKERS"] = sched[len("offload"):]
     os.environ["TINSEL_B200_CTA"] = cta

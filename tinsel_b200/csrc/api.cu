@@ -563,9 +563,13 @@ bool setup_offload(tb200_renderer* r, const SceneImage& img)
     r->numWalkers = 0;
     memset(&r->walk, 0, sizeof(r->walk));
     r->walk.treeletMesh = -1;
+    // Measured (profiles/README.md, round 2): with the walk offloaded ajax runs at 564 Msamples/s against 694
+    // inline (env 1950 / 3220, meshlight 254 / 325), so the mode is OFF unless asked for:
+    // TINSEL_B200_OFFLOAD=1 offloads every eligible mesh of more than 4096 triangles, =2 every mesh (tests).
     const char* env = getenv("TINSEL_B200_OFFLOAD");
-    const bool force = env && atoi(env) == 1;
-    if ((env && atoi(env) == 0) || r->hardPhases || sc.numFlat <= 0 || img.prims.size() > 16) return true;
+    const int want = env ? atoi(env) : 0;
+    const bool force = want == 2;
+    if (want <= 0 || r->hardPhases || sc.numFlat <= 0 || img.prims.size() > 16) return true;
     int bigMesh = -1, bigTris = 0;
     for (size_t i = 0; i < img.prims.size(); ++i) {
         const DPrim& p = img.prims[i];
@@ -681,8 +685,9 @@ bool upload_image(tb200_renderer* r, const SceneImage& img)
         if (cta && atoi(cta) == 768) r->wideCta = 1;
         if (cta && atoi(cta) == 512) r->wideCta = 0;
     }
-    if (!upload(img.prims, &r->dPrims, h2d)) return false;
-    if (!upload(img.scenePairs, &r->dScenePairs, h2d)) return false;
+    // one element of padding each: the kernels' bulk copies round their length up to 16 bytes
+    if (!upload(img.prims, &r->dPrims, h2d, 1)) return false;
+    if (!upload(img.scenePairs, &r->dScenePairs, h2d, 1)) return false;
 
     DScene& sc = r->scene;
     sc.prims = r->dPrims;
@@ -691,7 +696,7 @@ bool upload_image(tb200_renderer* r, const SceneImage& img)
     sc.numPairs = (int)img.scenePairs.size();
     static const std::vector<ProgOp> noFlat;
     const std::vector<ProgOp>& flat = getenv("TINSEL_B200_NO_FLAT") ? noFlat : img.flat;
-    if (!upload(flat, &r->dFlat, h2d)) return false;
+    if (!upload(flat, &r->dFlat, h2d, 1)) return false;
     sc.flat = r->dFlat;
     sc.numFlat = (int)flat.size();
     if (!setup_offload(r, img)) return false;

@@ -107,10 +107,11 @@ struct Wf2Shared {
     unsigned int ansHead[2];
     int ansPending[2];
     int exitSignaled;
-    // scene tables staged on chip
-    DPrim prims[TB_WF2_MAX_PRIMS];
-    BvhPair pairs[TB_WF2_MAX_PAIRS];
-    ProgOp flat[32];
+    // scene tables staged on chip by bulk copies (TMA) that complete on `stageBar`
+    alignas(16) DPrim prims[TB_WF2_MAX_PRIMS + 1];   // +1: the copy length is rounded up to 16 bytes
+    alignas(16) BvhPair pairs[TB_WF2_MAX_PAIRS];
+    alignas(16) ProgOp flat[32];
+    alignas(8) unsigned long long stageBar;
 };
 
 // dynamic shared memory of a CTA: the slot arrays; a build with fewer slots (experiments) still claims
@@ -455,28 +456,39 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     }
 
     // ---- prologue: stage the scene tables on chip ---------------------------------------------
+    // Primitive records, the scene-level BVH (child-pair records) and the flat scene program go from
+    // global to shared memory as TMA bulk copies (cp.async.bulk -> UBLKCP): thread 0 arms an mbarrier
+    // with the byte count and issues up to three copies, everybody waits on the barrier's phase.  (The
+    // walker CTAs of the offload mode stage the top of the big mesh's BVH the same way.)
     DScene sc = P.scene;
-    if (sc.numPrims <= TB_WF2_MAX_PRIMS) {
-        const int words = sc.numPrims * (int)(sizeof(DPrim) / 4);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.prims);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(S.prims);
-        for (int i = tid; i < words; i += THREADS) dst[i] = src[i];
-        sc.prims = S.prims;
+    const bool stagePrims = sc.numPrims <= TB_WF2_MAX_PRIMS;
+    const bool stagePairs = sc.numPairs > 0 && sc.numPairs <= TB_WF2_MAX_PAIRS;
+    const bool stageFlat = sc.numFlat > 0 && sc.numFlat <= 32;
+    if (tid == 0) {
+        const uint32_t bar = walk_smem_addr(&S.stageBar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // device arrays are padded by one element (api.cu: upload_image), so rounding up stays inside them
+        const uint32_t primBytes = stagePrims ? (((uint32_t)sc.numPrims * (uint32_t)sizeof(DPrim) + 15u) & ~15u) : 0u;
+        const uint32_t pairBytes = stagePairs ? (uint32_t)sc.numPairs * (uint32_t)sizeof(BvhPair) : 0u;
+        const uint32_t flatBytes = stageFlat ? (uint32_t)sc.numFlat * (uint32_t)sizeof(ProgOp) : 0u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(primBytes + pairBytes + flatBytes) : "memory");
+        if (primBytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(walk_smem_addr(S.prims)),
+                         "l"(P.scene.prims), "r"(primBytes), "r"(bar)
+                         : "memory");
+        if (pairBytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(walk_smem_addr(S.pairs)),
+                         "l"(P.scene.pairs), "r"(pairBytes), "r"(bar)
+                         : "memory");
+        if (flatBytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(walk_smem_addr(S.flat)),
+                         "l"(P.scene.flat), "r"(flatBytes), "r"(bar)
+                         : "memory");
     }
-    if (sc.numPairs <= TB_WF2_MAX_PAIRS) {
-        const int words = sc.numPairs * (int)(sizeof(BvhPair) / 4);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.pairs);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(S.pairs);
-        for (int i = tid; i < words; i += THREADS) dst[i] = src[i];
-        sc.pairs = S.pairs;
-    }
-    if (sc.numFlat > 0 && sc.numFlat <= 32) {
-        const int words = sc.numFlat * (int)(sizeof(ProgOp) / 4);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.scene.flat);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(S.flat);
-        for (int i = tid; i < words; i += THREADS) dst[i] = src[i];
-        sc.flat = S.flat;
-    }
+    if (stagePrims) sc.prims = S.prims;
+    if (stagePairs) sc.pairs = S.pairs;
+    if (stageFlat) sc.flat = S.flat;
     // every slot starts in the R queue "finished with nothing to splat": stage R fills it with a
     // camera sample
     for (int s = tid; s < TB_WF2_PATHS; s += THREADS) {
@@ -505,7 +517,15 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             S.ansHead[1] = walk_ld1(P.walk.ansTail + blockIdx.x * 2 + 1);
         }
     }
-    __syncthreads();
+    __syncthreads();   // the barrier word is initialised (thread 0, above) before anybody polls it
+    {
+        uint32_t landed = 0;
+        while (!landed)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(landed)
+                         : "r"(walk_smem_addr(&S.stageBar)), "r"(0u)
+                         : "memory");
+    }
 
     const int maxDepth = P.film.maxDepth;
     const int lane = tid & 31;
