@@ -83,3 +83,39 @@ def test_probe_tables_rebuilt_bit_exact():
         assert np.array_equal(_arr(getattr(a, f), cnt).view(np.uint32), _arr(getattr(b, f), cnt).view(np.uint32)), f
     ref.close()
     snap.close()
+
+
+def test_damaged_snapshots_are_refused_not_crashed(tmp_path):
+    """tb200_snapshot_load checks every count against the bytes left in the file before sizing an array from
+    it, and lets no exception cross the C ABI: truncated files, huge or negative counts give NULL + an error."""
+    import struct
+    data = open(tb.scene_path("glass"), "rb").read()
+    lib = tb.load_library()
+
+    def attempt(blob):
+        p = str(tmp_path / "bad.tsnap")
+        open(p, "wb").write(blob)
+        h = lib.tb200_snapshot_load(p.encode())
+        if h:
+            lib.tb200_snapshot_free(h)
+        return bool(h), tb.last_error()
+
+    assert attempt(data)[0]
+    for cut in (4, 20, 60, len(data) // 3, len(data) - 5):
+        ok, err = attempt(data[:cut])
+        assert not ok and "snapshot" in err, cut
+    # header: magic(8) + 6 x uint32 {primitives, meshes, bvh nodes, probe flag, probe w, probe h}
+    for field, value in ((0, 0x7FFFFFFF), (1, 0x40000000), (2, 0xFFFFFFFF), (3, 1)):
+        hdr = bytearray(data)
+        struct.pack_into("<I", hdr, 8 + 4 * field, value)
+        if field == 3:
+            struct.pack_into("<II", hdr, 8 + 16, 60000, 60000)   # a probe far larger than the file
+        ok, err = attempt(bytes(hdr))
+        assert not ok, field
+    # a mesh with a negative vertex count: first mesh record follows the primitives and the scene BVH
+    nprim, nmesh, nnodes = struct.unpack_from("<III", data, 8)
+    off = 8 + 24 + 40 + 48 + 24 + nprim * 180 + nnodes * 32   # sizeof(tb200_primitive) == 180
+    bad = bytearray(data)
+    struct.pack_into("<i", bad, off, -5)
+    ok, err = attempt(bytes(bad))
+    assert not ok

@@ -700,6 +700,21 @@ bool upload_image(tb200_renderer* r, const SceneImage& img)
     sc.flat = r->dFlat;
     sc.numFlat = (int)flat.size();
     if (!setup_offload(r, img)) return false;
+    // treelet: the top of the largest mesh's BVH is staged in shared memory by the wavefront kernel (meshes small
+    // enough to live in L1 gain nothing).  TINSEL_B200_TREELET=0 turns it off.
+    sc.treelet = nullptr;
+    sc.treeletMesh = -1;
+    sc.treeletPairs = 0;
+    {
+        const char* tl = getenv("TINSEL_B200_TREELET");
+        int big = -1;
+        for (size_t m = 0; m < img.meshes.size(); ++m)
+            if (img.meshes[m].numTris > 1024 && (big < 0 || img.meshes[m].numTris > img.meshes[big].numTris)) big = (int)m;
+        if (big >= 0 && !(tl && atoi(tl) == 0)) {
+            sc.treeletMesh = big;
+            sc.treeletPairs = (int)img.meshes[big].pairs.size();
+        }
+    }
     sc.rootRef = img.sceneRoot;
     sc.meshes = r->dMeshes;
     sc.numMeshes = (int)img.meshes.size();

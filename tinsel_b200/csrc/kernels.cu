@@ -291,6 +291,14 @@ void launch_nlm(const NlmParams& p, cudaStream_t stream, unsigned long long* lau
 #include <algorithm>
 #include <mutex>
 
+// dynamic shared memory a CTA may opt in to on the current device (227 KB on sm_100a)
+static size_t wavefront2_smem_limit()
+{
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) return 0;
+    return (size_t)v;
+}
+
 // offload mode (wavefront_walk.cuh): a launch uses it when the renderer set it up for this scene
 static inline bool wavefront2_wants_offload(const LaunchParams& p)
 {

@@ -54,6 +54,7 @@ struct LaunchParams {
     WalkParams walk;
     // cold half of the wavefront's slot state: 8 x float4 per slot, TB_WF2_PATHS slots per CTA of the launch
     float4* cold;
+    int treeletBytes;     // shared memory behind the slot arrays that the prologue fills with the top of DScene::treeletMesh's BVH
 };
 
 #define TB_MAX_BANDS 64

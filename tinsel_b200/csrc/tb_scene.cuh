@@ -104,6 +104,13 @@ struct DScene {
     // Offload mode of the wavefront kernel (wavefront_walk.cuh): bit i set = primitive i is a big mesh
     // whose BVH walk runs on the walker CTAs; trace_partial() skips it and reports the rays that reach it.
     uint32_t deferMask;
+    // Treelet: the first `treeletPairs` pair records (breadth-first = the top levels) of mesh `treeletMesh`'s BVH,
+    // staged in shared memory by the wavefront kernel's prologue (a TMA bulk copy); ray_mesh() reads records
+    // below that index from there.  The host sets treeletMesh and the mesh's total pair count; the kernel clips
+    // the count to the shared memory it has left and sets the pointer.  Null / 0 everywhere else.
+    const unsigned char* treelet;
+    int treeletPairs;
+    int treeletMesh;
 };
 
 struct Hit {
@@ -177,7 +184,7 @@ struct MeshHit {
 };
 
 // IntersectRayMesh + MeshQuery, intersection.h:629-749
-static __device__ __noinline__ bool ray_mesh(const DMesh& m, V3 origin, V3 dir, MeshHit& out)
+static __device__ __noinline__ bool ray_mesh(const DMesh& m, const unsigned char* top, uint32_t topCount, V3 origin, V3 dir, MeshHit& out)
 {
     V3 rcp;
     rcp.x = 1.0f / dir.x;
@@ -213,9 +220,12 @@ static __device__ __noinline__ bool ray_mesh(const DMesh& m, V3 origin, V3 dir, 
             }
             tmax = closestT;  // "truncate ray", intersection.h:700
         } else {
-            const BvhPair* pr = &m.pairs[ref];
-            const float4 a = __ldg(&pr->a), b = __ldg(&pr->b), c = __ldg(&pr->c);
-            const uint2 kids = __ldg(reinterpret_cast<const uint2*>(&pr->left));
+            // top of the tree from the staged treelet (shared memory), the rest from global memory: one generic
+            // load path for both (the treelet pointer is opaque to the compiler, see the kernel prologue)
+            const unsigned char* base = ref < topCount ? top : reinterpret_cast<const unsigned char*>(m.pairs);
+            const BvhPair* pr = reinterpret_cast<const BvhPair*>(base + (size_t)ref * sizeof(BvhPair));
+            const float4 a = pr->a, b = pr->b, c = pr->c;
+            const uint2 kids = *reinterpret_cast<const uint2*>(&pr->left);
             float tLeft, tRight;
             const bool hitLeft = ray_aabb(origin, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft) && tLeft < tmax;
             const bool hitRight = ray_aabb(origin, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight) && tRight < tmax;
@@ -282,7 +292,8 @@ TB_DEV bool prim_test(const DScene& sc, const DPrim& p, V3 o, V3 d, float time, 
     const V3 lo = inverse_transform_point(xf, o);
     const V3 ld = inverse_transform_vector(xf, d);
     MeshHit mh;
-    if (!ray_mesh(sc.meshes[p.mesh], lo, ld, mh)) return false;
+    const bool staged = p.mesh == sc.treeletMesh && sc.treelet != nullptr;
+    if (!ray_mesh(sc.meshes[p.mesh], sc.treelet, staged ? (uint32_t)sc.treeletPairs : 0u, lo, ld, mh)) return false;
     ph.t = mh.t;
     ph.tri = mh.tri;
     ph.u = mh.u;

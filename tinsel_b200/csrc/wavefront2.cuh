@@ -472,7 +472,19 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
         const uint32_t primBytes = stagePrims ? (((uint32_t)sc.numPrims * (uint32_t)sizeof(DPrim) + 15u) & ~15u) : 0u;
         const uint32_t pairBytes = stagePairs ? (uint32_t)sc.numPairs * (uint32_t)sizeof(BvhPair) : 0u;
         const uint32_t flatBytes = stageFlat ? (uint32_t)sc.numFlat * (uint32_t)sizeof(ProgOp) : 0u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(primBytes + pairBytes + flatBytes) : "memory");
+        const bool stageTreelet = P.treeletBytes >= (int)sizeof(BvhPair) && P.scene.treeletMesh >= 0;
+        const uint32_t treeBytes = stageTreelet ? (uint32_t)min(P.scene.treeletPairs, P.treeletBytes / (int)sizeof(BvhPair)) * (uint32_t)sizeof(BvhPair) : 0u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(primBytes + pairBytes + flatBytes + treeBytes) : "memory");
+        if (treeBytes) {
+            unsigned char* tl = wf_smem_raw + ((sizeof(Wf2Shared) + 127) & ~size_t(127));
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(P.scene.meshes[P.scene.treeletMesh].pairs);
+            for (uint32_t off = 0; off < treeBytes; off += 32768u) {
+                const uint32_t n = min(32768u, treeBytes - off);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(walk_smem_addr(tl + off)),
+                             "l"(src + off), "r"(n), "r"(bar)
+                             : "memory");
+            }
+        }
         if (primBytes)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(walk_smem_addr(S.prims)),
                          "l"(P.scene.prims), "r"(primBytes), "r"(bar)
@@ -489,6 +501,17 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     if (stagePrims) sc.prims = S.prims;
     if (stagePairs) sc.pairs = S.pairs;
     if (stageFlat) sc.flat = S.flat;
+    // the top of the biggest mesh's BVH goes into whatever shared memory the slot arrays leave (P.treeletBytes,
+    // set by the launch from the device's limit): the first levels of every inline mesh walk are then shared-
+    // memory reads instead of dependent L2 round trips
+    sc.treelet = nullptr;
+    if (P.treeletBytes >= (int)sizeof(BvhPair) && sc.treeletMesh >= 0) {
+        unsigned char* tl = wf_smem_raw + ((sizeof(Wf2Shared) + 127) & ~size_t(127));
+        sc.treeletPairs = min(sc.treeletPairs, P.treeletBytes / (int)sizeof(BvhPair));
+        sc.treelet = walk_opaque(tl);
+    } else {
+        sc.treeletPairs = 0;
+    }
     // every slot starts in the R queue "finished with nothing to splat": stage R fills it with a
     // camera sample
     for (int s = tid; s < TB_WF2_PATHS; s += THREADS) {
@@ -927,7 +950,8 @@ static int wavefront2_ctas_per_sm()
     std::lock_guard<std::mutex> guard(lock);
     if (ctasPerSM[dev] == 0) {
         int n = 0;
-        cudaFuncSetAttribute(k_wavefront2<THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_WF2_SMEM_BYTES);
+        cudaFuncSetAttribute(k_wavefront2<THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)std::max(wavefront2_smem_limit(), (size_t)TB_WF2_SMEM_BYTES));
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wavefront2<THREADS, MODE>, THREADS, TB_WF2_SMEM_BYTES) != cudaSuccess || n < 1)
             n = 1;
         if (n > TB_WF2_MAX_CTAS_PER_SM) n = TB_WF2_MAX_CTAS_PER_SM;
@@ -937,9 +961,18 @@ static int wavefront2_ctas_per_sm()
 }
 
 template <int THREADS, int MODE>
-static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long total)
+static void launch_wavefront2_t(const LaunchParams& p0, int numSMs, cudaStream_t stream, unsigned long long total)
 {
     const int ctasPerSM = wavefront2_ctas_per_sm<THREADS, MODE>();
+    // shared memory beyond the slot arrays holds the treelet (the shader role; walker CTAs lay out their own)
+    LaunchParams p = p0;
+    const size_t slotBytes = (TB_WF2_SMEM_BYTES + 127) & ~size_t(127);
+    p.treeletBytes = 0;
+    if (p.scene.treeletMesh >= 0 && p.scene.treeletPairs > 0 && MODE != WF2_MODE_OFFLOAD && wavefront2_smem_limit() > slotBytes) {
+        const size_t room = (wavefront2_smem_limit() - slotBytes) / sizeof(BvhPair) * sizeof(BvhPair);
+        p.treeletBytes = (int)std::min(room, (size_t)p.scene.treeletPairs * sizeof(BvhPair));
+    }
+    const size_t smemBytes = p.treeletBytes > 0 ? slotBytes + (size_t)p.treeletBytes : TB_WF2_SMEM_BYTES;
     // TB_WF2_CTAS_PER_SM resident CTAs per SM; small jobs use fewer so that every CTA has a full slot array
     const unsigned long long want = (total + TB_WF2_PATHS - 1) / TB_WF2_PATHS;
     int grid = (numSMs > 0 ? numSMs : 148) * ctasPerSM;
@@ -951,12 +984,12 @@ static void launch_wavefront2_t(const LaunchParams& p, int numSMs, cudaStream_t 
         if (want < (unsigned long long)shaders) shaders = (int)std::max<unsigned long long>(1ull, want);
         q.walk.numShaders = shaders;
         q.walk.numWalkers = walkers;
-        k_wavefront2<THREADS, MODE><<<shaders + walkers, THREADS, TB_WF2_SMEM_BYTES, stream>>>(q, total);
+        k_wavefront2<THREADS, MODE><<<shaders + walkers, THREADS, smemBytes, stream>>>(q, total);
         return;
     }
     if (want < (unsigned long long)grid) grid = (int)want;
     if (grid < 1) grid = 1;
-    k_wavefront2<THREADS, MODE><<<grid, THREADS, TB_WF2_SMEM_BYTES, stream>>>(p, total);
+    k_wavefront2<THREADS, MODE><<<grid, THREADS, smemBytes, stream>>>(p, total);
 }
 
 // the launches of this layout (see the top of the file for which scheduler variants each layout serves)
