@@ -700,8 +700,11 @@ bool upload_image(tb200_renderer* r, const SceneImage& img)
     sc.flat = r->dFlat;
     sc.numFlat = (int)flat.size();
     if (!setup_offload(r, img)) return false;
-    // treelet: the top of the largest mesh's BVH is staged in shared memory by the wavefront kernel (meshes small
-    // enough to live in L1 gain nothing).  TINSEL_B200_TREELET=0 turns it off.
+    // treelet: the top of the largest mesh's BVH staged in the shared memory the slot arrays leave, for the INLINE
+    // mesh walk.  Measured (profiles/README.md round 2, step 29): slower on every scene -- ajax 629 vs 689, env
+    // 2858 vs 3067, meshlight 371 vs 402 Msamples/s -- because the top levels already live in L1, and claiming the
+    // last 45 KB of shared memory shrinks L1 from 60 to 28 KB.  Off unless TINSEL_B200_TREELET=1.  (The walker CTAs
+    // of the offload mode always stage theirs: they have nothing else in shared memory.)
     sc.treelet = nullptr;
     sc.treeletMesh = -1;
     sc.treeletPairs = 0;
@@ -710,7 +713,7 @@ bool upload_image(tb200_renderer* r, const SceneImage& img)
         int big = -1;
         for (size_t m = 0; m < img.meshes.size(); ++m)
             if (img.meshes[m].numTris > 1024 && (big < 0 || img.meshes[m].numTris > img.meshes[big].numTris)) big = (int)m;
-        if (big >= 0 && !(tl && atoi(tl) == 0)) {
+        if (big >= 0 && tl && atoi(tl) == 1) {
             sc.treeletMesh = big;
             sc.treeletPairs = (int)img.meshes[big].pairs.size();
         }
