@@ -167,77 +167,6 @@ uint32_t build_pairs(const tb200_bvh_node* nodes, int numNodes, std::vector<BvhP
     return ref_of(0);
 }
 
-// Collapsed 4-wide tree over the same boxes (tb_scene.cuh: BvhQuad, ray_mesh4): every interior node adopts its
-// grandchildren -- the child with the larger surface area is opened first -- until it has four children or only
-// leaves.  Returns the root reference; *maxStack = the deepest stack the near-first walk can need.
-uint32_t build_quads(const tb200_bvh_node* nodes, int numNodes, std::vector<BvhQuad>* out, int* maxStack)
-{
-    out->clear();
-    *maxStack = 0;
-    if (numNodes <= 0) return TB_LEAF;
-    if (nodes[0].right_leaf >> 31) return TB_LEAF | nodes[0].left;
-    auto is_leaf = [&](uint32_t i) { return (nodes[i].right_leaf >> 31) != 0; };
-    auto area = [&](uint32_t i) {
-        const float ex = nodes[i].upper[0] - nodes[i].lower[0], ey = nodes[i].upper[1] - nodes[i].lower[1], ez = nodes[i].upper[2] - nodes[i].lower[2];
-        return ex * ey + ey * ez + ez * ex;
-    };
-    struct Item { uint32_t node; uint32_t quad; int depth; };
-    std::vector<Item> todo;
-    out->emplace_back();
-    todo.push_back({0u, 0u, 1});
-    int deepest = 1;
-    std::vector<char> seen(numNodes, 0);
-    seen[0] = 1;
-    while (!todo.empty()) {
-        const Item it = todo.back();
-        todo.pop_back();
-        deepest = std::max(deepest, it.depth);
-        uint32_t kids[4] = {nodes[it.node].left, nodes[it.node].right_leaf & 0x7fffffffu, 0u, 0u};
-        int n = 2;
-        while (n < 4) {
-            int open = -1;
-            for (int k = 0; k < n; ++k)
-                if (!is_leaf(kids[k]) && (open < 0 || area(kids[k]) > area(kids[open]))) open = k;
-            if (open < 0) break;
-            const uint32_t o = kids[open];
-            kids[open] = nodes[o].left;
-            kids[n++] = nodes[o].right_leaf & 0x7fffffffu;
-        }
-        BvhQuad q;
-        memset(&q, 0, sizeof(q));
-        float* lo[3] = {&q.lox.x, &q.loy.x, &q.loz.x};
-        float* hi[3] = {&q.hix.x, &q.hiy.x, &q.hiz.x};
-        for (int k = 0; k < 4; ++k) {
-            if (k >= n) {
-                q.ref[k] = TB_NO_CHILD;
-                for (int a = 0; a < 3; ++a) {   // an empty box: never hit, whatever the ray
-                    lo[a][k] = FLT_MAX;
-                    hi[a][k] = -FLT_MAX;
-                }
-                continue;
-            }
-            const tb200_bvh_node& c = nodes[kids[k]];
-            for (int a = 0; a < 3; ++a) {
-                lo[a][k] = c.lower[a];
-                hi[a][k] = c.upper[a];
-            }
-            if (is_leaf(kids[k])) {
-                q.ref[k] = TB_LEAF | c.left;
-            } else if (seen[kids[k]]) {
-                q.ref[k] = TB_NO_CHILD;   // malformed input (a node reachable twice): drop the repeat
-            } else {
-                seen[kids[k]] = 1;
-                q.ref[k] = (uint32_t)out->size();
-                out->emplace_back();
-                todo.push_back({kids[k], q.ref[k], it.depth + 1});
-            }
-        }
-        (*out)[it.quad] = q;
-    }
-    *maxStack = deepest * 3 + 1;
-    return 0u;   // the root quad
-}
-
 // Flat scene program for trace_closest() (tb_scene.cuh).  Walks the scene BVH once; infinite
 // boxes (planes' +-1e8 bounds and every ancestor of one) are transparent, finite interior boxes get
 // a bit in the per-ray mask, leaves become LEAF / LEAFBOX / PLANE ops guarded by the bit of their
@@ -497,8 +426,6 @@ struct MeshImage {
     int numTris = 0;
     uint32_t rootRef = TB_LEAF;
     int depth = 0;
-    std::vector<BvhQuad> quads;   // collapsed 4-wide tree (empty: not used)
-    uint32_t rootRef4 = TB_LEAF;
 };
 
 struct SceneImage {
@@ -527,14 +454,6 @@ bool image_from_scene(const tb200_scene* s, SceneImage* img)
         const tb200_mesh& g = s->meshes[m];
         MeshImage& mi = img->meshes[m];
         mi.rootRef = build_pairs(g.nodes, g.numNodes, &mi.pairs, &mi.depth);
-        {
-            int maxStack = 0;
-            mi.rootRef4 = build_quads(g.nodes, g.numNodes, &mi.quads, &maxStack);
-            if (maxStack > 64 || mi.quads.empty()) {   // ray_mesh4's stack; single-triangle meshes have no interior node
-                mi.quads.clear();
-                mi.rootRef4 = TB_LEAF;
-            }
-        }
         const int numTris = g.numIndices / 3;
         mi.numTris = numTris;
         img->maxTris = std::max(img->maxTris, numTris);
@@ -723,14 +642,9 @@ bool upload_image(tb200_renderer* r, const SceneImage& img)
         BvhPair* dPairs;
         float4 *dVerts, *dNorms;
         float* dCdf;
-        BvhQuad* dQuads = nullptr;
-        const bool wide = !mi.quads.empty() && !(getenv("TINSEL_B200_BVH4") && atoi(getenv("TINSEL_B200_BVH4")) == 0);
         if (!upload(mi.pairs, &dPairs, h2d) || !upload(mi.verts, &dVerts, h2d) || !upload(mi.norms, &dNorms, h2d) ||
-            !upload(mi.cdf, &dCdf, h2d) || (wide && !upload(mi.quads, &dQuads, h2d)))
+            !upload(mi.cdf, &dCdf, h2d))
             return false;
-        r->owned.push_back(dQuads);
-        meshes[m].quads = dQuads;
-        meshes[m].rootRef4 = mi.rootRef4;
         r->owned.push_back(dPairs);
         r->owned.push_back(dVerts);
         r->owned.push_back(dNorms);
@@ -844,10 +758,10 @@ bool build_scene(tb200_renderer* r, const tb200_scene* s)
 // a stamp mismatch is refused and the caller falls back to tb200_create), then the SceneImage fields in
 // declaration order; every array as a 64-bit count followed by its bytes.
 const char kCacheMagic[8] = {'T', 'B', '2', 'C', 'A', 'C', 'H', 'E'};
-const uint32_t kCacheVersion = 3;
+const uint32_t kCacheVersion = 2;
 
 struct CacheStamp {
-    uint32_t version, sizeofPrim, sizeofPair, sizeofOp;   // (BvhQuad rides on the version)
+    uint32_t version, sizeofPrim, sizeofPair, sizeofOp;
 };
 
 template <typename T>
@@ -881,7 +795,7 @@ bool image_save(const SceneImage& img, const char* path)
     ok = ok && put_pod(f, numMeshes);
     for (const MeshImage& m : img.meshes)
         ok = ok && put_vec(f, m.pairs) && put_vec(f, m.verts) && put_vec(f, m.norms) && put_vec(f, m.cdf) && put_pod(f, m.numTris) &&
-             put_pod(f, m.rootRef) && put_pod(f, m.depth) && put_vec(f, m.quads) && put_pod(f, m.rootRef4);
+             put_pod(f, m.rootRef) && put_pod(f, m.depth);
     ok = ok && put_pod(f, img.horizon) && put_pod(f, img.zenith) && put_pod(f, img.numNee) && put_pod(f, img.maxTris) &&
          put_pod(f, img.splitBoxValid) && put_pod(f, img.splitLo) && put_pod(f, img.splitHi);
     ok = ok && put_pod(f, img.probeValid) && put_pod(f, img.probeW) && put_pod(f, img.probeH) && put_vec(f, img.probeData) &&
@@ -913,8 +827,7 @@ bool image_load(const char* path, SceneImage* img)
     for (size_t m = 0; ok && m < img->meshes.size(); ++m) {
         MeshImage& mi = img->meshes[m];
         ok = get_vec(f, &mi.pairs, fileBytes) && get_vec(f, &mi.verts, fileBytes) && get_vec(f, &mi.norms, fileBytes) &&
-             get_vec(f, &mi.cdf, fileBytes) && get_pod(f, &mi.numTris) && get_pod(f, &mi.rootRef) && get_pod(f, &mi.depth) &&
-             get_vec(f, &mi.quads, fileBytes) && get_pod(f, &mi.rootRef4);
+             get_vec(f, &mi.cdf, fileBytes) && get_pod(f, &mi.numTris) && get_pod(f, &mi.rootRef) && get_pod(f, &mi.depth);
     }
     ok = ok && get_pod(f, &img->horizon) && get_pod(f, &img->zenith) && get_pod(f, &img->numNee) && get_pod(f, &img->maxTris) &&
          get_pod(f, &img->splitBoxValid) && get_pod(f, &img->splitLo) && get_pod(f, &img->splitHi);
@@ -941,10 +854,6 @@ bool validate_image(const SceneImage& img, std::string* why)
         if (!ref_ok(m.rootRef, m.pairs.size(), nt)) return *why = "mesh root reference out of range", false;
         for (const BvhPair& p : m.pairs)
             if (!ref_ok(p.left, m.pairs.size(), nt) || !ref_ok(p.right, m.pairs.size(), nt)) return *why = "mesh BVH reference out of range", false;
-        if (!m.quads.empty() && !ref_ok(m.rootRef4, m.quads.size(), nt)) return *why = "mesh 4-wide root reference out of range", false;
-        for (const BvhQuad& q : m.quads)
-            for (int k = 0; k < 4; ++k)
-                if (q.ref[k] != TB_NO_CHILD && !ref_ok(q.ref[k], m.quads.size(), nt)) return *why = "mesh 4-wide BVH reference out of range", false;
     }
     for (const DPrim& p : img.prims) {
         if (p.type != TB200_SPHERE && p.type != TB200_PLANE && p.type != TB200_MESH) return *why = "unknown primitive type", false;

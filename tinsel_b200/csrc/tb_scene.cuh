@@ -35,17 +35,6 @@ struct __align__(16) BvhPair {
     uint32_t pad0, pad1;
 };
 
-// Four-wide node of the COLLAPSED mesh BVH (api.cu: build_quads): the reference's binary tree with every other
-// level folded away, so that a walk takes half as many dependent fetches.  128 bytes = one cache line:
-// the four children's boxes as six float4 (component-major) and their references ((leaf<<31)|index,
-// 0xffffffff = no child).  Only ray_mesh4() reads it; the binary pairs stay for the reference-order walk.
-#define TB_NO_CHILD 0xffffffffu
-struct __align__(16) BvhQuad {
-    float4 lox, loy, loz, hix, hiy, hiz;
-    uint32_t ref[4];
-    uint32_t pad[4];
-};
-
 struct DMaterial {
     V3 emission;
     V3 color;
@@ -69,8 +58,6 @@ struct DMesh {
     const float* cdf;
     int numTris;
     uint32_t rootRef;
-    const BvhQuad* quads;       // collapsed 4-wide tree (nullptr: walk the binary pairs)
-    uint32_t rootRef4;
 };
 
 struct DPrim {
@@ -260,112 +247,6 @@ static __device__ __noinline__ bool ray_mesh(const DMesh& m, const unsigned char
     return false;
 }
 
-// The same closest hit through the collapsed 4-wide tree, in ANY order -- half the dependent fetches of the
-// binary walk.  Why the result is still the reference's, bit for bit:
-//  * every box here is a box of the reference's tree and the slab test is the reference's, which is monotone
-//    in the box (a ray that passes a child's box passes every ancestor's) as long as no product is NaN -- the
-//    caller sends rays with a zero direction component through the binary walk -- so the triangles reached are a
-//    superset of those the reference reaches before distance culling;
-//  * distance culling (`t <= closestT` here, `tLeft < tmax` there) only drops boxes that lie beyond the closest
-//    hit found so far, so both walks find the same minimal t with the strict `t < closestT` -- UNLESS two
-//    candidates are within rounding of each other: the winner between two triangles at (nearly) the same t, and
-//    whether a box whose entry distance is within a few ulps of a hit gets opened, depend on the visit order.
-//    Every such case is caught: a triangle hit within 4e-6 (relative) of the best one, or a box culled within
-//    that margin of it, sets `uncertain`, and the caller redoes the ray with the reference-order walk.  Organic
-//    meshes (ajax) almost never trigger it; axis-aligned geometry, where a face's coplanar neighbour enters at
-//    the hit distance, triggers it on about half of its rays and simply walks twice.
-#define TB_NEAR 1.000004f
-static __device__ __noinline__ bool ray_mesh4(const DMesh& m, V3 origin, V3 dir, MeshHit& out, bool& uncertain)
-{
-    V3 rcp;
-    rcp.x = 1.0f / dir.x;
-    rcp.y = 1.0f / dir.y;
-    rcp.z = 1.0f / dir.z;
-
-    uint32_t stack[64];   // api.cu refuses trees that could need more (3 pushes per level)
-    int count = 0;
-    uint32_t cur = m.rootRef4;
-    float closestT = FLT_MAX;
-    out.tri = -1;
-    uncertain = false;
-
-    for (;;) {
-        if (cur & TB_LEAF) {
-            const uint32_t i = cur & ~TB_LEAF;
-            const float4 q0 = __ldg(&m.triVerts[i * 3 + 0]);
-            const float4 q1 = __ldg(&m.triVerts[i * 3 + 1]);
-            const float4 q2 = __ldg(&m.triVerts[i * 3 + 2]);
-            float t, u, v, w, sign;
-            V3 n;
-            if (ray_tri(origin, dir, v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), v3(q1.z, q1.w, q2.x), t, u, v, w, sign, n)) {
-                if (t > 0.0f) {
-                    if (t < closestT) {
-                        if (closestT <= t * TB_NEAR) uncertain = true;   // the previous best was within rounding of this one
-                        closestT = t;
-                        out.u = u;
-                        out.v = v;
-                        out.w = w;
-                        out.tri = (int)i;
-                        out.n = n * sign;
-                    } else if (t <= closestT * TB_NEAR) {
-                        uncertain = true;
-                    }
-                }
-            }
-        } else {
-            const BvhQuad* q = &m.quads[cur];
-            const float4 lox = __ldg(&q->lox), loy = __ldg(&q->loy), loz = __ldg(&q->loz);
-            const float4 hix = __ldg(&q->hix), hiy = __ldg(&q->hiy), hiz = __ldg(&q->hiz);
-            const uint4 refs = __ldg(reinterpret_cast<const uint4*>(q->ref));
-            float t0, t1, t2, t3;
-            bool h0 = ray_aabb(origin, rcp, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, t0);
-            bool h1 = refs.y != TB_NO_CHILD && ray_aabb(origin, rcp, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, t1);
-            bool h2 = refs.z != TB_NO_CHILD && ray_aabb(origin, rcp, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, t2);
-            bool h3 = refs.w != TB_NO_CHILD && ray_aabb(origin, rcp, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, t3);
-            // distance culling, with the near-miss margin (see above)
-            const float lim = closestT * TB_NEAR;
-            if (h0 && t0 > closestT) { uncertain = uncertain || t0 <= lim; h0 = false; }
-            if (h1 && t1 > closestT) { uncertain = uncertain || t1 <= lim; h1 = false; }
-            if (h2 && t2 > closestT) { uncertain = uncertain || t2 <= lim; h2 = false; }
-            if (h3 && t3 > closestT) { uncertain = uncertain || t3 <= lim; h3 = false; }
-            // near-first: sort the (entry distance, reference) pairs ascending, misses last (5 compare-exchanges)
-            float k0 = h0 ? t0 : FLT_MAX, k1 = h1 ? t1 : FLT_MAX, k2 = h2 ? t2 : FLT_MAX, k3 = h3 ? t3 : FLT_MAX;
-            uint32_t r0 = h0 ? refs.x : TB_NO_CHILD, r1 = h1 ? refs.y : TB_NO_CHILD, r2 = h2 ? refs.z : TB_NO_CHILD, r3 = h3 ? refs.w : TB_NO_CHILD;
-#define TB_CSWAP(ka, ra, kb, rb)                   \
-    {                                              \
-        const bool sw = kb < ka;                   \
-        const float kt = sw ? kb : ka;             \
-        const uint32_t rt = sw ? rb : ra;          \
-        kb = sw ? ka : kb;                         \
-        rb = sw ? ra : rb;                         \
-        ka = kt;                                   \
-        ra = rt;                                   \
-    }
-            TB_CSWAP(k0, r0, k1, r1)
-            TB_CSWAP(k2, r2, k3, r3)
-            TB_CSWAP(k0, r0, k2, r2)
-            TB_CSWAP(k1, r1, k3, r3)
-            TB_CSWAP(k1, r1, k2, r2)
-#undef TB_CSWAP
-            // r0 is the nearest hit child (or none); the others wait on the stack, farthest first
-            if (r3 != TB_NO_CHILD) stack[count++] = r3;
-            if (r2 != TB_NO_CHILD) stack[count++] = r2;
-            if (r1 != TB_NO_CHILD) stack[count++] = r1;
-            if (r0 != TB_NO_CHILD) {
-                cur = r0;
-                continue;
-            }
-        }
-        if (count == 0) break;
-        cur = stack[--count];
-    }
-    if (out.tri >= 0) {
-        out.t = closestT;
-        return true;
-    }
-    return false;
-}
-
 // PrimitiveIntersect, intersection.h:951-1020, split in two: prim_test() decides hit / t exactly
 // as the reference does, prim_normal() produces *outNormal for a recorded hit.  The reference
 // computes the normal of every candidate (no side effects); only the winner's is ever used, so
@@ -411,19 +292,8 @@ TB_DEV bool prim_test(const DScene& sc, const DPrim& p, V3 o, V3 d, float time, 
     const V3 lo = inverse_transform_point(xf, o);
     const V3 ld = inverse_transform_vector(xf, d);
     MeshHit mh;
-    const DMesh& mesh = sc.meshes[p.mesh];
     const bool staged = p.mesh == sc.treeletMesh && sc.treelet != nullptr;
-    bool hit, redo = true;
-    // (direction components of at least 1e-30 in magnitude: finite reciprocals, no 0 * inf in the slab tests, which
-    // is what makes them monotone in the box; NaNs fail the comparisons)
-    if (mesh.quads != nullptr && !staged && fabsf(ld.x) >= 1.0e-30f && fabsf(ld.y) >= 1.0e-30f && fabsf(ld.z) >= 1.0e-30f) {
-        // the 4-wide walk; anything within rounding of a tie goes back to the reference-order walk
-        bool uncertain;
-        hit = ray_mesh4(mesh, lo, ld, mh, uncertain);
-        redo = uncertain;
-    }
-    if (redo) hit = ray_mesh(mesh, sc.treelet, staged ? (uint32_t)sc.treeletPairs : 0u, lo, ld, mh);
-    if (!hit) return false;
+    if (!ray_mesh(sc.meshes[p.mesh], sc.treelet, staged ? (uint32_t)sc.treeletPairs : 0u, lo, ld, mh)) return false;
     ph.t = mh.t;
     ph.tri = mh.tri;
     ph.u = mh.u;
