@@ -1062,9 +1062,13 @@ bool render_streamed(tb200_renderer* r, LaunchParams& P, float* output, bool rec
         // unfinished samples sit in local tile rows >= done*bandTileRows, i.e. global pixel rows
         // >= firstRow + done*bandTileRows*numShards*4 (decode_sample)
         copy_rows_below(P.firstRow + done * bandTileRows * P.numShards * 4 - reach);
-        if (cudaEventQuery(r->evStop) != cudaErrorNotReady) break;   // finished (or failed): stop polling
+        // The band flags (plain reads of mapped host memory) are the signal; the event is only the safety net for a
+        // launch that failed -- and a driver call per spin from every device's thread of a multi-device renderer
+        // contends on the driver's locks, so it is asked rarely.
+        ++spins;
+        if ((spins & 1023u) == 0u && cudaEventQuery(r->evStop) != cudaErrorNotReady) break;   // finished (or failed): stop polling
         // back off: the calling thread may be the host application's UI thread (tinsel's GLUT loop)
-        if (++spins < 64u)
+        if (spins < 4096u)
             __builtin_ia32_pause();
         else
             std::this_thread::yield();

@@ -632,13 +632,22 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             }
         } else {
             int p = 0;
-            if (lane == 0) p = *(volatile int*)&S.pref;
+            if (lane == 0) p = *(volatile int*)&S.pref | (*(volatile int*)&S.exhausted << 8);
             p = __shfl_sync(0xffffffffu, p, 0);
+            // Once the sample counter has run dry the CTA is draining: nothing refills the queues any more, so
+            // waiting for full 32-entry chunks only adds latency -- take whatever is there.  (A 1-spp Render() on
+            // one of N GPUs is ALL drain: a single partial fill of the slot arrays.)
+#ifdef TB_WF2_NO_DRAIN
+            const int full = 32;
+#else
+            const int full = (p >> 8) ? 1 : 32;
+#endif
+            p &= 0xff;
             if (offload) {
                 // sweep over six sources: T, answers(ext), A, answers(shadow), B, R
                 for (int k = 0; k < WALK_SWEEP_PASSES * 6 && stage < 0; ++k) {
                     const int pos = (p + k) % 6;
-                    const int minCount = k < 6 ? 32 : (k < 12 ? WALK_PARTIAL_MIN : 1);
+                    const int minCount = k < 6 ? full : (k < 12 ? WALK_PARTIAL_MIN : 1);
                     if (pos == 1 || pos == 3) {
                         n = wf2_claim_answers(S, P.walk, pos == 1 ? WALK_KIND_EXT : WALK_KIND_SHADOW, minCount, ans0, ans1, ans2);
                         if (n > 0) {
@@ -657,7 +666,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                 for (int k = 0; k < 8 && stage < 0; ++k) {
                     // k = 0..3: full chunks only; k = 4..7: whatever is left
                     const int q = (p + k) & 3;
-                    n = wf2_claim(S, q, k < 4 ? 32 : 1, s);
+                    n = wf2_claim(S, q, k < 4 ? full : 1, s);
                     if (n > 0) stage = q;
                 }
             } else {
@@ -665,7 +674,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
                 for (int k = 0; k < 10 && stage < 0; ++k) {
                     const int pos = (p + k) % 5;
                     const int q = pos == 0 ? WF2_Q_T : pos == 1 ? WF2_Q_TM : pos == 2 ? WF2_Q_A : pos == 3 ? WF2_Q_B : WF2_Q_R;
-                    n = wf2_claim(S, q, k < 5 ? 32 : 1, s);
+                    n = wf2_claim(S, q, k < 5 ? full : 1, s);
                     if (n > 0) {
                         stage = q;
                         if (pos != p && lane == 0) *(volatile int*)&S.pref = pos;
