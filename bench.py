@@ -487,7 +487,11 @@ def run_ours(args):
             m.Render(cam, opt, host)
         e2e_dt = time.time() - t0
         assert np.isfinite(host).all() and float(host[..., 3].min()) > 0.0   # every row was delivered by its owner
-        e2e = {"value": W * H * calls / e2e_dt / 1e6, "unit": "Msamples/s",
+        per_device = []
+        for k in range(world):
+            st, row0, rows = m.member_stats(k)
+            per_device.append({"device": k, "rows": [row0, row0 + rows], "kernel_ms_last_call": round(st.gpuMs, 4)})
+        e2e = {"value": W * H * calls / e2e_dt / 1e6, "unit": "Msamples/s", "per_device": per_device,
                "h2d_bytes_per_step": E2E_CALLS_PER_STEP * (C.sizeof(tb.Camera) + C.sizeof(tb.Options)),
                "d2h_bytes_per_step": E2E_CALLS_PER_STEP * W * H * 16,
                "calls_per_step": E2E_CALLS_PER_STEP, "ms_per_call": e2e_dt / calls * 1e3,

@@ -283,6 +283,10 @@ void tb200_set_frame(tb200_renderer* r, int frame);
 
 void tb200_get_stats(tb200_renderer* r, tb200_stats* out);
 
+/* The counters of ONE member of a multi-device renderer (0 = the head) and the pixel rows it owns: how the
+ * work of the last call was spread (gpuMs per device).  Returns 0 on success. */
+int tb200_get_member_stats(tb200_renderer* r, int member, tb200_stats* out, int* firstRow, int* numRows);
+
 /* Deletes the renderer and all its device memory (reference: `delete g_renderer`, src/main.cpp:323). */
 void tb200_destroy(tb200_renderer* r);
 

@@ -84,6 +84,8 @@ def load_library():
     lib.tb200_set_frame.argtypes = [C.c_void_p, C.c_int]
     lib.tb200_get_stats.restype = None
     lib.tb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    lib.tb200_get_member_stats.restype = C.c_int
+    lib.tb200_get_member_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(Stats), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.tb200_destroy.restype = None
     lib.tb200_destroy.argtypes = [C.c_void_p]
     lib.tb200_last_error.restype = C.c_char_p
@@ -237,6 +239,12 @@ class Renderer:
 
     def num_devices(self):
         return self.lib.tb200_num_devices(self.h)
+
+    def member_stats(self, member):
+        """(Stats, first_row, num_rows) of one device of a multi-device renderer."""
+        st, a, b = Stats(), C.c_int(), C.c_int()
+        self._check(self.lib.tb200_get_member_stats(self.h, member, C.byref(st), C.byref(a), C.byref(b)), "tb200_get_member_stats")
+        return st, a.value, b.value
 
     def bind_accumulator(self, device_ptr):
         self._check(self.lib.tb200_bind_accumulator(self.h, C.c_void_p(device_ptr)), "tb200_bind_accumulator")

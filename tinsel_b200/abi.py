@@ -160,6 +160,7 @@ EXPORTS = [
     "tb200_create_cached",
     "tb200_scene_cache_save",
     "tb200_num_devices",
+    "tb200_get_member_stats",
     "tb200_slab_rows",
     "tb200_slab_traced_rows",
     "tb200_set_slab",

@@ -1952,6 +1952,21 @@ void tb200_get_stats(tb200_renderer* r, tb200_stats* out)
     }
 }
 
+int tb200_get_member_stats(tb200_renderer* r, int member, tb200_stats* out, int* firstRow, int* numRows)
+{
+    if (!r || !out || member < 0 || member > (int)r->peers.size()) {
+        set_error("tb200_get_member_stats: bad argument");
+        return -1;
+    }
+    const tb200_renderer* m = member == 0 ? r : r->peers[member - 1];
+    *out = m->stats;
+    int row0, row1;
+    owned_rows(m, &row0, &row1);
+    if (firstRow) *firstRow = row0;
+    if (numRows) *numRows = row1 - row0;
+    return 0;
+}
+
 void tb200_destroy(tb200_renderer* r)
 {
     if (!r) return;
