@@ -49,8 +49,8 @@
 #define TB_WF2_CTAS_PER_SM 1
 #endif
 static_assert(TB_WF2_PATHS <= TB_WF2_SLOTS, "the host sizes the cold slot state and the offload queues with TB_WF2_SLOTS");
-#define TB_WF2_MAX_PRIMS 16     // scene tables up to this size are staged in shared memory
-#define TB_WF2_MAX_PAIRS 16
+#define TB_WF2_MAX_PRIMS 40     // scene tables up to this size are staged in shared memory (the flat program: up to 16 primitives)
+#define TB_WF2_MAX_PAIRS 40
 
 enum { WF2_PH_EXT = 0, WF2_PH_NEE = 1 };
 #define WF2_FLAG_EMPTY 1u   // the slot holds no sample (before its first camera ray)
