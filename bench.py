@@ -292,16 +292,23 @@ def measure_one_gpu(tb, torch, np, scene, w, h, spp, steps, warmup, device, flus
             clocks.start()
         launches0 = r.stats().kernelLaunches
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        lib_ms = []
         for i in range(steps):
             flush.fill_(i & 0xff)                       # evict L2 between timed steps (same stream, not timed)
             ev[i][0].record(stream)
             r.render_device(cam, opt, spp)              # synchronous: returns when the step's kernels are done
             ev[i][1].record(stream)
+            lib_ms.append(r.stats().gpuMs)              # the library's own CUDA events around the launch, same stream
         torch.cuda.synchronize()
         if clocks:
             clocks.stop_flag = True
             clocks.join(timeout=2)
-        step_ms = [a.elapsed_time(b) for a, b in ev]
+        # Two event pairs bracket every step on the launching stream: torch's, recorded from Python around the call,
+        # and the library's, recorded in C right around the launch.  The first also counts the host's delay between
+        # recording the event and launching the kernel (tens of microseconds; milliseconds when eight ranks share a
+        # CPU quota), so the step time is the library's and torch's is reported next to it.
+        torch_ms = [a.elapsed_time(b) for a, b in ev]
+        step_ms = lib_ms
         launches = r.stats().kernelLaunches - launches0
         img = r.read_accumulator()
     value = w * h * spp * steps / sum(step_ms) / 1e3
@@ -330,7 +337,7 @@ def measure_one_gpu(tb, torch, np, scene, w, h, spp, steps, warmup, device, flus
     assert abs(float(host[4:-4, 4:-4, 3].mean()) / (expect / (spp * steps) * (calls + 3)) - 1.0) < 0.01
     r.close()
     snap.close()
-    res = {"value": value, "step_ms": step_ms, "launches": launches,
+    res = {"value": value, "step_ms": step_ms, "torch_event_ms": torch_ms, "launches": launches,
            "e2e_value": w * h * calls / e2e_dt / 1e6, "e2e_ms_per_call": e2e_dt / calls * 1e3, "e2e_calls": calls,
            "cam_opt_bytes": C.sizeof(tb.Camera) + C.sizeof(tb.Options)}
     if clocks:
@@ -360,7 +367,8 @@ def run_ours(args):
         line = {
             "metric": "Msamples/sec (paths x spp / s)", "value": value, "unit": "Msamples/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": sum(step_ms) / args.steps, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": sum(step_ms) / args.steps, "ms_per_step_torch_events": sum(res["torch_event_ms"]) / args.steps,
+            "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (scene snapshot, random paths)",
             "config": workload_config(scene, W, H, SPP, 1),
             "clocks": res["clocks"],
@@ -442,11 +450,13 @@ def run_ours(args):
     clocks.start()
     launches0 = r.stats().kernelLaunches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
+    lib_ms = []
     for i in range(args.steps):
         flush.fill_(i & 0xff)
         ev[i][0].record(stream)
         r.render_device(cam, opt, SPP)
         ev[i][1].record(stream)
+        lib_ms.append(r.stats().gpuMs)
     # the reduce is timed from a common start: without the barrier, its events on the early ranks would also
     # count the time they wait for a rank whose host thread was descheduled between two steps (4 ms seen at N = 8)
     barrier()
@@ -456,7 +466,8 @@ def run_ours(args):
     barrier()
     clocks.stop_flag = True
     clocks.join(timeout=2)
-    step_ms = [a.elapsed_time(b) for a, b in ev[:args.steps]]
+    torch_ms = [a.elapsed_time(b) for a, b in ev[:args.steps]]
+    step_ms = lib_ms       # the library's events around the launch (see measure_one_gpu)
     reduce_ms = ev[args.steps][0].elapsed_time(ev[args.steps][1])
     dev_ms = sum(step_ms) + reduce_ms
     launches = r.stats().kernelLaunches - launches0
@@ -468,6 +479,11 @@ def run_ours(args):
     dev_ms = float(tmax[0])
     launches = int(tsum[1])
     value = W * H * SPP * args.steps / dev_ms / 1e3
+    # every rank's clocks and its own device time: on a shared 8-GPU box single GPUs have been seen 25-35 % slower
+    # than their neighbours under full load, and the max over ranks is what `value` reports
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"rank": rank, "steps_ms": round(sum(step_ms), 3), "steps_ms_torch_events": round(sum(torch_ms), 3),
+                                      "clocks": clocks.summary()}, group=host_group)
     if rank == 0:
         img = accum.cpu().numpy()
         assert np.isfinite(img).all() and float(img[..., :3].sum()) > 0.0
@@ -512,7 +528,7 @@ def run_ours(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (scene snapshot, random paths)",
             "config": workload_config(scene, W, H, SPP, world),
-            "clocks": clocks.summary(),
+            "clocks": dict(clocks.summary(), per_rank=per_rank),
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": roofline_block(scene, value / world, avg_launch_s, per_launch_samples, clocks.summary().get("sm_mhz")),
