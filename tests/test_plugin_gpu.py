@@ -42,6 +42,36 @@ def test_plugin_render_matches_seeded_oracle(name):
 
 
 @pytest.mark.gpu
+def test_plugin_multi_gpu_factory(monkeypatch):
+    """TINSEL_GPUS=N: CreateGpuWavefrontRenderer builds the multi-device renderer (row slabs, every member
+    delivers its own rows into the caller's Color buffer); Init / Render through the reference vtable as
+    before.  On a one-GPU box the members share device 0 (test hook)."""
+    import torch
+    if not os.path.exists(PLUGIN) or not refdrv.have_ref("detmath"):
+        pytest.skip("plugin or oracle/_ref not built")
+    os.environ.pop("TINSEL_B200_PIPELINE", None)
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        n = 3
+        monkeypatch.setenv("TINSEL_B200_TEST_DUP_DEVICES", "1")
+    monkeypatch.setenv("TINSEL_GPUS", str(n))
+    ref = refdrv.RefScene.from_snapshot(tb.scene_path("cornell"), "detmath")
+    ref.set_size(128, 100)
+    lib = C.CDLL(PLUGIN)
+    lib.tb200_plugin_render.restype = C.c_int
+    lib.tb200_plugin_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+    out = np.full((100, 128, 4), -3.0, np.float32)
+    rc = lib.tb200_plugin_render(ref.lib.ref_native_scene(ref.h), ref.lib.ref_native_camera(ref.h),
+                                 ref.lib.ref_native_options(ref.h), 5, out.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0
+    oracle = ref.render_seeded(0, 5, 4)
+    rel = np.linalg.norm((out - oracle).astype(np.float64)) / np.linalg.norm(oracle.astype(np.float64))
+    assert rel <= 1e-4, rel
+    assert np.allclose(out[..., 3], oracle[..., 3], rtol=1e-5, atol=1e-6)   # every row was delivered by its owner
+    ref.close()
+
+
+@pytest.mark.gpu
 def test_plugin_fast_paths_render_n_and_finish(tmp_path):
     """TinselB200RenderN + TinselB200Finish (tinsel_b200_plugin.h) on a reference Scene, against the
     reference's own finish loop and PNG writer applied to the sums the call returned."""

@@ -348,8 +348,6 @@ struct tb200_renderer {
     void* dWalkBlock = nullptr;   // one allocation behind every pointer of `walk`
     size_t walkBlockBytes = 0;
     int numWalkers = 0;           // 0: the offload mode is off
-    std::vector<int> meshDepth;   // interior levels of every mesh BVH
-    std::vector<int> meshPairs;   // BvhPair records of every mesh
 
     int pipeline = 2;             // 0 = mega (validation), 2 = wavefront (product)
     int hardPhases = 1;           // wavefront scheduling mode (see wavefront2.cuh)

@@ -125,7 +125,8 @@ struct GpuWavefrontRenderer : public Renderer {
         const int n = gpus ? atoi(gpus) : 1;
         if (n > 1) {
             std::vector<int> devices;
-            for (int k = 0; k < n; ++k) devices.push_back(k);
+            const bool oneGpuBox = getenv("TINSEL_B200_TEST_DUP_DEVICES") != nullptr;   // test hook: all members on device 0
+            for (int k = 0; k < n; ++k) devices.push_back(oneGpuBox ? 0 : k);
             impl = tb200_create_multi(&xs, devices.data(), n);
         } else {
             impl = tb200_create(&xs, dev ? atoi(dev) : 0);
