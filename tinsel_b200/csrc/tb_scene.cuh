@@ -184,6 +184,22 @@ struct MeshHit {
 };
 
 // IntersectRayMesh + MeshQuery, intersection.h:629-749
+//
+// The lanes of a warp that walk a mesh together do it in PHASES, chosen by vote among them (TB_MESH_PHASES):
+//   BOX  interior-node steps, repeated while most of the lanes have one.  A lane that reaches a triangle parks
+//        it in `pend` and keeps descending -- speculatively: its later box tests use a stale, larger tmax, so it
+//        visits a superset of the reference's nodes; everything in the extra nodes lies at t >= the closest hit
+//        and fails the strict `t < closestT`, and triangles are still tested in the reference's order, so the
+//        result is the reference's bit for bit (the walker CTAs of wavefront_walk.cuh run the same scheme);
+//   TRI  the parked triangles are tested.
+// A data-dependent `if (leaf) ... else ...` per lane makes the warp execute both bodies in almost every
+// iteration; this way each pass runs one body with the lanes that are ready for it.  Measured (profiles/README.md
+// round 2, step 32): bit-exact, but the votes cost more than the divergence they remove -- ajax 678 vs 690, table
+// 186 vs 200, cornell 1074 vs 1099 Msamples/s -- so the plain loop below is the default (-DTB_MESH_PHASES=1 builds
+// the voted one; the walker CTAs of the offload mode, which have nothing else to do, keep theirs).
+#ifndef TB_MESH_PHASES
+#define TB_MESH_PHASES 0
+#endif
 static __device__ __noinline__ bool ray_mesh(const DMesh& m, const unsigned char* top, uint32_t topCount, V3 origin, V3 dir, MeshHit& out)
 {
     V3 rcp;
@@ -192,13 +208,90 @@ static __device__ __noinline__ bool ray_mesh(const DMesh& m, const unsigned char
     rcp.z = 1.0f / dir.z;
 
     uint32_t stack[TB_STACK];
-    stack[0] = m.rootRef;
-    int count = 1;
-
     float closestT = FLT_MAX;
     float tmax = FLT_MAX;
     out.tri = -1;
-
+#if TB_MESH_PHASES
+    const uint32_t EMPTY = 0xffffffffu;
+    const unsigned mask = __activemask();   // the lanes that entered together; every vote below is among them
+    const int group = __popc(mask);
+    const int boxMin = (group * 5 + 7) / 8, triMin = (group + 3) / 4;
+    int sp = 0;
+    uint32_t cur = m.rootRef, pend = EMPTY;
+    if (cur & TB_LEAF) {   // a one-triangle mesh
+        pend = cur;
+        cur = EMPTY;
+    }
+    for (;;) {
+        // ---- BOX ---------------------------------------------------------------------------------------------
+        int nBox;
+        for (;;) {
+            const bool wBox = cur != EMPTY && (cur & TB_LEAF) == 0u;
+            nBox = __popc(__ballot_sync(mask, wBox));
+            if (nBox == 0) break;
+            if (wBox) {
+                // IntersectRayMesh interior step, intersection.h:702-727; top of the tree from the staged treelet
+                // (shared memory) when there is one, the rest from global memory: one generic load path for both
+                const unsigned char* base = cur < topCount ? top : reinterpret_cast<const unsigned char*>(m.pairs);
+                const BvhPair* pr = reinterpret_cast<const BvhPair*>(base + (size_t)cur * sizeof(BvhPair));
+                const float4 a = pr->a, b = pr->b, c = pr->c;
+                const uint2 kids = *reinterpret_cast<const uint2*>(&pr->left);
+                float tLeft, tRight;
+                const bool hitLeft = ray_aabb(origin, rcp, a.x, a.y, a.z, a.w, b.x, b.y, tLeft) && tLeft < tmax;
+                const bool hitRight = ray_aabb(origin, rcp, b.z, b.w, c.x, c.y, c.z, c.w, tRight) && tRight < tmax;
+                // "traverse closest first": the reference pushes the far child, then the near one, and pops the near
+                // one at once (intersection.h:716-727) -- the near child is next, the far one goes on the stack
+                const bool both = hitLeft && hitRight;
+                const bool swap = both && (tLeft < tRight);
+                const uint32_t far = swap ? kids.y : kids.x;
+                uint32_t nxt = both ? (swap ? kids.x : kids.y) : (hitLeft ? kids.x : kids.y);
+                if (both) stack[sp++] = far;
+                if (!(hitLeft || hitRight)) nxt = sp > 0 ? stack[--sp] : EMPTY;
+                if (nxt != EMPTY && (nxt & TB_LEAF) != 0u && pend == EMPTY) {
+                    // park the triangle, go on with what the reference would pop after testing it
+                    pend = nxt;
+                    nxt = sp > 0 ? stack[--sp] : EMPTY;
+                }
+                cur = nxt;
+            }
+            if (nBox < boxMin) break;   // give the triangle phase a turn (one step per turn keeps every lane progressing)
+        }
+        // ---- TRI ---------------------------------------------------------------------------------------------
+        const bool wTri = pend != EMPTY;
+        const int nPend = __popc(__ballot_sync(mask, wTri));
+        if (nPend > 0 && (nPend >= triMin || nBox < boxMin)) {
+            if (wTri) {
+                // MeshQuery, intersection.h:629-674
+                const uint32_t i = pend & ~TB_LEAF;
+                const float4 q0 = __ldg(&m.triVerts[i * 3 + 0]);
+                const float4 q1 = __ldg(&m.triVerts[i * 3 + 1]);
+                const float4 q2 = __ldg(&m.triVerts[i * 3 + 2]);
+                float t, u, v, w, sign;
+                V3 n;
+                if (ray_tri(origin, dir, v3(q0.x, q0.y, q0.z), v3(q0.w, q1.x, q1.y), v3(q1.z, q1.w, q2.x), t, u, v, w, sign, n)) {
+                    if (t > 0.0f && t < closestT) {
+                        closestT = t;
+                        out.u = u;
+                        out.v = v;
+                        out.w = w;
+                        out.tri = (int)i;
+                        out.n = n * sign;
+                    }
+                }
+                tmax = closestT;   // "truncate ray", intersection.h:700
+                pend = EMPTY;
+                if (cur != EMPTY && (cur & TB_LEAF) != 0u) {
+                    // a second triangle was waiting behind the first
+                    pend = cur;
+                    cur = sp > 0 ? stack[--sp] : EMPTY;
+                }
+            }
+        }
+        if (__ballot_sync(mask, cur != EMPTY || pend != EMPTY) == 0u) break;   // every lane of the group is done
+    }
+#else
+    stack[0] = m.rootRef;
+    int count = 1;
     while (count) {
         const uint32_t ref = stack[--count];
         if (ref & TB_LEAF) {
@@ -220,8 +313,6 @@ static __device__ __noinline__ bool ray_mesh(const DMesh& m, const unsigned char
             }
             tmax = closestT;  // "truncate ray", intersection.h:700
         } else {
-            // top of the tree from the staged treelet (shared memory), the rest from global memory: one generic
-            // load path for both (the treelet pointer is opaque to the compiler, see the kernel prologue)
             const unsigned char* base = ref < topCount ? top : reinterpret_cast<const unsigned char*>(m.pairs);
             const BvhPair* pr = reinterpret_cast<const BvhPair*>(base + (size_t)ref * sizeof(BvhPair));
             const float4 a = pr->a, b = pr->b, c = pr->c;
@@ -240,6 +331,7 @@ static __device__ __noinline__ bool ray_mesh(const DMesh& m, const unsigned char
             if (hitRight) stack[count++] = right;
         }
     }
+#endif
     if (closestT < FLT_MAX) {
         out.t = closestT;
         return true;
