@@ -109,8 +109,13 @@ def _check_group(devices, name="cornell", size=(256, 192)):
     assert np.array_equal(rad.view(np.uint32), rad1.view(np.uint32)) and np.array_equal(ras, ras1)
     with pytest.raises(tb.TinselB200Error):
         m.set_shard(0, 2)
+    # destroying the group must not touch the caller's buffer (a worker thread once re-ran its last job on the
+    # way out and rendered one more frame into it)
+    m.Render(cam, opt, out)
+    before = out.copy()
     m.unpin_output()
     m.close()
+    assert np.array_equal(out.view(np.uint32), before.view(np.uint32))
     r1.close()
     snap.close()
 

@@ -1091,7 +1091,8 @@ struct Worker {
     std::condition_variable wake;
     std::function<int(tb200_renderer*)> job;
     std::atomic<uint32_t> posted{0}, done{0};
-    bool sleeping = false, quit = false;
+    bool sleeping = false;
+    std::atomic<bool> quit{false};
     int rc = 0;
 };
 
@@ -1111,11 +1112,13 @@ void worker_main(tb200_renderer* r)
             }
             std::unique_lock<std::mutex> guard(w->lock);
             w->sleeping = true;
-            w->wake.wait(guard, [&] { return w->posted.load(std::memory_order_acquire) != seen || w->quit; });
+            w->wake.wait(guard, [&] { return w->posted.load(std::memory_order_acquire) != seen || w->quit.load(); });
             w->sleeping = false;
-            if (w->quit) return;
             spins = 0;
         }
+        // tb200_destroy bumps `posted` to get a spinning worker out of its loop: that is not a job (the last one is
+        // still in `job` -- running it again would render one more frame into a buffer the caller may have freed)
+        if (w->quit.load(std::memory_order_acquire)) return;
         seen += 1;
         g_error.clear();
         w->rc = w->job(r);
@@ -1973,7 +1976,7 @@ void tb200_destroy(tb200_renderer* r)
     if (r->worker) {
         {
             std::lock_guard<std::mutex> guard(r->worker->lock);
-            r->worker->quit = true;
+            r->worker->quit.store(true, std::memory_order_release);
         }
         r->worker->posted.fetch_add(1, std::memory_order_release);   // leave the spin, see `quit`
         r->worker->wake.notify_one();
