@@ -213,16 +213,18 @@ def test_max_depth_edge_cases(depth, pipeline):
 
 
 @pytest.mark.parametrize("cta", ["512", "768"])
-@pytest.mark.parametrize("sched", ["hard", "free", "split", "treelet", "offload", "offload1", "offload100"])
+@pytest.mark.parametrize("sched", ["hard", "free", "ring", "split", "treelet", "offload", "offload1", "offload100"])
 def test_both_scheduling_modes_bit_exact(sched, cta):
     """Every scheduler variant x CTA size of the wavefront kernel (the per-scene heuristics of
     api.cu build_scene pick one of them) produces the same bits: hard phases, free running, free
     running with the split trace queue forced on for every scene that has a mesh, and the mesh-walk
     offload (shader CTAs + walker CTAs, wavefront_walk.cuh) forced on for every mesh, with the
     default number of walker CTAs, a single one, and as many as fit; "treelet" = free running with the top
-    of the biggest mesh's BVH staged in shared memory for the inline walk."""
+    of the biggest mesh's BVH staged in shared memory for the inline walk.  "free" at 512 threads runs the
+    lane-owned slot layout with bit-set queues on every scene without a split queue, "ring" the ring queues."""
     offload = sched.startswith("offload")
-    os.environ["TINSEL_B200_SCHED"] = "free" if sched in ("split", "treelet") or offload else sched
+    os.environ["TINSEL_B200_SCHED"] = "free" if sched in ("split", "treelet", "ring") or offload else sched
+    os.environ["TINSEL_B200_QUEUES"] = "ring" if sched == "ring" else "lanes"
     os.environ["TINSEL_B200_TREELET"] = "1" if sched == "treelet" else "0"   # top of the biggest mesh's BVH TMA-staged for the inline walk
     os.environ["TINSEL_B200_SPLIT"] = "1" if sched == "split" else "0"
     os.environ["TINSEL_B200_OFFLOAD"] = "2" if offload else "0"
@@ -242,7 +244,8 @@ def test_both_scheduling_modes_bit_exact(sched, cta):
             ref.close()
             snap.close()
     finally:
-        for k in ("TINSEL_B200_SCHED", "TINSEL_B200_SPLIT", "TINSEL_B200_CTA", "TINSEL_B200_OFFLOAD", "TINSEL_B200_WALKERS", "TINSEL_B200_TREELET"):
+        for k in ("TINSEL_B200_SCHED", "TINSEL_B200_SPLIT", "TINSEL_B200_CTA", "TINSEL_B200_OFFLOAD", "TINSEL_B200_WALKERS", "TINSEL_B200_TREELET",
+                  "TINSEL_B200_QUEUES"):
             os.environ.pop(k, None)
 
 

@@ -352,6 +352,7 @@ struct tb200_renderer {
     int pipeline = 2;             // 0 = mega (validation), 2 = wavefront (product)
     int hardPhases = 1;           // wavefront scheduling mode (see wavefront2.cuh)
     int wideCta = 0;              // 768-thread CTAs for deep mesh BVHs (see wavefront2.cuh)
+    int laneQueues = 0;           // lane-owned slots + bit-set queues (see wavefront2.cuh)
     // Split trace queue on/off is decided by measurement (every variant produces the same bits): the
     // second and third sizeable launches after tb200_create time one setting each, the faster stays.
     int tunePhase = 3;            // 0 warm-up (split), 1 measuring split, 2 measuring no split, 3 decided
@@ -682,6 +683,11 @@ bool upload_image(tb200_renderer* r, const SceneImage& img)
         const char* cta = getenv("TINSEL_B200_CTA");
         if (cta && atoi(cta) == 768) r->wideCta = 1;
         if (cta && atoi(cta) == 512) r->wideCta = 0;
+        // Lane-owned slots with bit-set queues: scenes held on chip under the free-running scheduler (the launch
+        // falls back to the ring queues for every other combination).  TINSEL_B200_QUEUES=ring|lanes.
+        r->laneQueues = 1;
+        const char* queues = getenv("TINSEL_B200_QUEUES");
+        if (queues && strcmp(queues, "ring") == 0) r->laneQueues = 0;
     }
     // one element of padding each: the kernels' bulk copies round their length up to 16 bytes
     if (!upload(img.prims, &r->dPrims, h2d, 1)) return false;
@@ -902,6 +908,7 @@ bool fill_params(tb200_renderer* r, const tb200_camera* camera, const tb200_opti
     P->cold = r->dCold;
     P->hardPhases = r->hardPhases;
     P->wideCta = r->wideCta;
+    P->laneQueues = r->laneQueues;
     P->firstRow = 0;
     P->numRows = o->height;
     P->film.rowLo = 0;

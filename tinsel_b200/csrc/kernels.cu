@@ -305,12 +305,15 @@ static inline bool wavefront2_wants_offload(const LaunchParams& p)
     return p.walk.numWalkers > 0 && !p.hardPhases && p.scene.deferMask != 0u && p.scene.numFlat > 0;
 }
 
-// Two layouts of the wavefront's slot state, one compilation of wavefront2.cuh each:
+// Three layouts of the wavefront's slot state and queues, one compilation of wavefront2.cuh each:
 //  * wf2_smem: 1024 slots per CTA, hot + cold state in shared memory.  Scenes held on chip (cornell, veach):
 //    they are issue-bound, and fetching the cold half from L2 costs them 4-10 %.
 //  * wf2_l2: 2048 slots per CTA, the cold half (27 of 45 words) in a 128-byte record per slot in global
 //    memory, L2-resident.  Scenes with deep mesh BVHs (ajax +6 %, env +8 %) and the offload mode: their
 //    rays take long, and twice the paths in flight hide it.
+//  * wf2_lq: wf2_smem's state with LANE-OWNED slots and bit-set stage queues instead of rings, free-running
+//    scheduler only: no shared-memory bank conflicts and far cheaper queue operations, at the price of the
+//    rings' FIFO order (scenes held on chip do not care: cornell +11 %; deep BVHs do: ajax -5 %).
 namespace wf2_smem {
 #undef TB_WF2_PATHS
 #define TB_WF2_PATHS 1024
@@ -323,11 +326,22 @@ namespace wf2_l2 {
 #define TB_WF2_PATHS 2048
 #include "wavefront2.cuh"
 }  // namespace wf2_l2
+namespace wf2_lq {
+#undef TB_WF2_PATHS
+#define TB_WF2_PATHS 1024
+#define TB_WF2_COLD_SMEM 1
+#define TB_WF2_LANEQ 1
+#include "wavefront2.cuh"
+#undef TB_WF2_LANEQ
+#undef TB_WF2_COLD_SMEM
+}  // namespace wf2_lq
 
 void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
 {
     if (p.wideCta || wavefront2_wants_offload(p))
         wf2_l2::launch_layout(p, numSMs, stream, launchCount);
+    else if (p.laneQueues && !p.hardPhases && !p.scene.splitValid)
+        wf2_lq::launch_layout(p, numSMs, stream, launchCount);
     else
         wf2_smem::launch_layout(p, numSMs, stream, launchCount);
 }

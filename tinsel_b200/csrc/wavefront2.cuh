@@ -32,12 +32,16 @@
 // ticket claims for scenes where every hit spawns several shadow rays; and free-running with a
 // second trace queue for rays that enter a big mesh.
 //
-// This header is compiled TWICE by kernels.cu, in two namespaces, for the two layouts of the slot state
-// (chosen with TB_WF2_PATHS / TB_WF2_COLD_SMEM before each inclusion; see kernels.cu):
-//   wf2_smem  1024 slots per CTA, the whole state in shared memory -- scenes held on chip, 512-thread CTAs
-//   wf2_l2    2048 slots per CTA, the cold half of the state in global memory (L2) -- scenes with deep
-//             mesh BVHs (768-thread CTAs, and the offload mode), which gain from more paths in flight
-// so it has no include guard, and only defines macros whose text is the same both times.
+// This header is compiled THREE TIMES by kernels.cu, in three namespaces, for the three layouts of the slot
+// state and its queues (chosen with TB_WF2_PATHS / TB_WF2_COLD_SMEM / TB_WF2_LANEQ before each inclusion):
+//   wf2_smem  1024 slots per CTA, the whole state in shared memory, ring queues -- scenes held on chip under
+//             the hard-phase scheduler (several shadow rays per hit), 512-thread CTAs
+//   wf2_lq    the same state with LANE-OWNED slots and bit-set queues (see wf2_push) -- scenes held on chip
+//             under the free-running scheduler: no bank conflicts, cheap queue operations, no FIFO order
+//   wf2_l2    2048 slots per CTA, the cold half of the state in global memory (L2), ring queues -- scenes with
+//             deep mesh BVHs (768-thread CTAs, and the offload mode), which gain from more paths in flight
+//             and from the rings' FIFO order (rays pushed together are traced together)
+// so it has no include guard, and only defines macros whose text is the same every time.
 
 #ifndef TB_WF2_THREADS
 #define TB_WF2_THREADS 512
@@ -95,10 +99,15 @@ struct Wf2Shared {
 #ifdef TB_WF2_COLD_SMEM
     float4 cold[TB_WF2_PATHS * 7];
 #endif
+#ifdef TB_WF2_LANEQ
+    // stage queues as bit sets (lane-owned slots, see wf2_push below): one word per queue and lane
+    unsigned int lq[4][32];
+#else
     // stage queues: rings of lap-tagged slot ids
     uint16_t ring[7][TB_WF2_PATHS];
     unsigned int head[7], tail[7];
     unsigned int snap[5];             // hard-phase mode: the tail each stage of the current phase runs with
+#endif
     int pref;                         // stage the warps currently prefer (soft phases, see the main loop)
     int live;                         // slots that still hold (or may still receive) a path
     int exhausted;
@@ -142,6 +151,25 @@ TB_DEV uint16_t wf2_cell(unsigned int index, int slot)
     return (uint16_t)((unsigned)slot | (lap << WF2_SLOT_BITS));
 }
 
+#ifdef TB_WF2_LANEQ
+// Lane-owned slots (the third layout, wf2_lq: scenes held on chip, free-running warps).  Slot s is only ever
+// handled by lane (s & 31) of whichever warp claims it, so every access to the slot arrays is free of bank
+// conflicts (lane i touches bank i; with ring queues the slot ids of a chunk are a random permutation and 35 %
+// of the kernel's shared-memory wavefronts were conflicts), and a stage queue needs no ring: it is one bit per
+// slot, the 32 slots of a lane in one word.  A push is one atomicOr by the owning lane on its own word -- no
+// ballot, no prefix sum, no reserved-but-unwritten cell for a consumer to trip over.  The price is the FIFO
+// order (a chunk is no longer a run of rays that were pushed together), which costs scenes with deep BVHs
+// their traversal coherence: those keep the ring queues.
+// The caller has fenced its slot-state writes (__threadfence_block).
+static_assert(TB_WF2_PATHS == 1024, "one word per lane and queue");
+#ifndef WF2_STICK_LANES
+#define WF2_STICK_LANES 16     // a warp stays with the preferred stage while that many lanes have a slot waiting there
+#endif
+TB_DEV void wf2_push(Wf2Shared& S, int q, bool flag, int slot)
+{
+    if (flag) atomicOr(&S.lq[q][slot & 31], 1u << (slot >> 5));
+}
+#else
 // append `slot` to stage queue q for every lane with flag == true: ballot + prefix sum, one shared
 // atomic per warp.  The caller has fenced its slot-state writes (__threadfence_block).
 TB_DEV void wf2_push(Wf2Shared& S, int q, bool flag, int slot)
@@ -158,6 +186,7 @@ TB_DEV void wf2_push(Wf2Shared& S, int q, bool flag, int slot)
         *(volatile uint16_t*)&S.ring[q][idx & WF2_MASK] = wf2_cell(idx, slot);
     }
 }
+#endif
 
 // Push a slot whose pending ray is ready to be traced.  With `split` set the ray (extension ray, or
 // the shadow ray from the hit point) is classified against the big mesh's bounds first; the test
@@ -187,6 +216,61 @@ TB_DEV void wf2_push_trace(Wf2Shared& S, const DScene& sc, bool split, int q, bo
     wf2_push(S, WF2_Q_TM, flag && big, s);
 }
 
+#ifdef TB_WF2_LANEQ
+// Claim one waiting slot per lane.  All four queues (T, A, B, R) are looked at in one go -- four independent
+// loads of the lane's own words and four ballots -- and the warp takes the CTA's preferred stage while at least
+// `stick` lanes have something there, else the stage with the most lanes ready (which becomes the preference:
+// the warps of a CTA herd through the stages, and share the instruction cache -- a per-warp preference instead
+// of the CTA-wide one costs 35 %).  Every lane then picks a set bit of its word -- starting at a position that
+// differs from warp to warp, so that two warps claiming at once rarely want the same one -- and clears it with
+// an atomicAnd; whoever sees the bit set in the value returned owns the slot.  Returns the mask of lanes that
+// got a slot (0: nothing waits anywhere) and the stage.
+TB_DEV unsigned wf2_claim_fullest(Wf2Shared& S, int stick, int& slot, int& stage)
+{
+    const int lane = threadIdx.x & 31;
+    const int rot = (int)(threadIdx.x >> 5) * 2 + 1;
+    for (;;) {
+        // the preference and the four queue words load side by side (no load depends on another)
+        int pref = 0;
+        if (lane == 0) pref = *(volatile int*)&S.pref;
+        const unsigned m0 = *(volatile unsigned int*)&S.lq[0][lane], m1 = *(volatile unsigned int*)&S.lq[1][lane];
+        const unsigned m2 = *(volatile unsigned int*)&S.lq[2][lane], m3 = *(volatile unsigned int*)&S.lq[3][lane];
+        pref = __shfl_sync(0xffffffffu, pref, 0);
+        // lanes ready per queue, one byte each (selections by shifts, not branches)
+        const unsigned cc = (unsigned)__popc(__ballot_sync(0xffffffffu, m0 != 0u)) | ((unsigned)__popc(__ballot_sync(0xffffffffu, m1 != 0u)) << 8) |
+                            ((unsigned)__popc(__ballot_sync(0xffffffffu, m2 != 0u)) << 16) | ((unsigned)__popc(__ballot_sync(0xffffffffu, m3 != 0u)) << 24);
+        int q = pref;
+        unsigned bc = (cc >> (8 * pref)) & 0xffu;
+        if (bc < (unsigned)stick) {
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                const int qq = (pref + k) & 3;
+                const unsigned cq = (cc >> (8 * qq)) & 0xffu;
+                q = cq > bc ? qq : q;
+                bc = cq > bc ? cq : bc;
+            }
+        }
+        if (bc == 0u) return 0u;
+        const unsigned lo = (q & 1) ? m1 : m0, hi = (q & 1) ? m3 : m2;
+        const unsigned mine = (q & 2) ? hi : lo;
+        bool got = false;
+        if (mine != 0u) {
+            const int k = (__ffs(__funnelshift_r(mine, mine, rot)) - 1 + rot) & 31;
+            const unsigned bit = 1u << k;
+            got = (atomicAnd(&S.lq[q][lane], ~bit) & bit) != 0u;
+            slot = lane + 32 * k;
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, got);
+        if (act != 0u) {
+            __threadfence_block();   // the producer's state writes precede its atomicOr
+            if (q != pref && lane == 0) *(volatile int*)&S.pref = q;
+            stage = q;
+            return act;
+        }
+        // every lane lost its bit to another warp, which made progress: look again
+    }
+}
+#else
 // Claim up to 32 entries of queue q for this warp.  Returns the number claimed (warp-uniform);
 // lane i < n receives its slot.  Lock-free: cells are read first, ownership is taken with a CAS
 // on head, so a stalled warp can never read a cell that a producer has already recycled.
@@ -242,6 +326,10 @@ TB_DEV int wf2_claim_ticket(Wf2Shared& S, int q, unsigned int tail, int& slot)
     if (lane < n) slot = (int)(*(volatile uint16_t*)&S.ring[q][(base + (unsigned)lane) & WF2_MASK] & WF2_SLOT_MASK);
     return n;
 }
+
+// the same claims as lane masks (lanes 0..n-1), the form the kernel body works with
+TB_DEV unsigned wf2_lanes(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+#endif
 
 TB_DEV Surface wf2_surface(const Wf2Shared& S, const DScene& sc, int s, float eta)
 {
@@ -514,6 +602,11 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     }
     // every slot starts in the R queue "finished with nothing to splat": stage R fills it with a
     // camera sample
+#ifdef TB_WF2_LANEQ
+    for (int s = tid; s < TB_WF2_PATHS; s += THREADS) S.flags[s] = WF2_FLAG_EMPTY;
+    if (tid < 4 * 32) S.lq[tid >> 5][tid & 31] = (tid >> 5) == WF2_Q_R ? 0xffffffffu : 0u;
+    if (tid == 0) {
+#else
     for (int s = tid; s < TB_WF2_PATHS; s += THREADS) {
         S.ring[WF2_Q_R][s] = wf2_cell((unsigned)s, s);
         S.ring[WF2_Q_T][s] = 0;
@@ -529,6 +622,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
         S.tail[WF2_Q_R] = TB_WF2_PATHS;
         S.snap[0] = TB_WF2_PATHS;
         S.snap[1] = S.snap[2] = S.snap[3] = S.snap[4] = 0u;
+#endif
         S.pref = WF2_Q_R;
         S.live = TB_WF2_PATHS;
         S.exhausted = 0;
@@ -574,6 +668,22 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
     //    CTA-wide preferred stage and moving on cyclically when that queue has no full chunk left
     //    (dragging the preference along).  Nobody ever waits for a slow ray, which wins when ray
     //    cost varies wildly (deep mesh BVHs) and the hot loop is small enough to stay cached.
+#ifdef TB_WF2_LANEQ
+    static_assert(MODE == WF2_MODE_GENERIC, "the lane-owned layout serves the free-running scheduler only");
+    constexpr bool hard = false, split = false;
+    const int cycle = 0;
+    for (;;) {
+        int s = 0, stage = -1;
+        const bool fromAnswer = false;
+        const uint4 ans0 = make_uint4(0u, 0u, 0u, 0u), ans1 = ans0, ans2 = ans0;
+        const unsigned act = wf2_claim_fullest(S, WF2_STICK_LANES, s, stage);
+        if (act == 0u) {
+            if (*(volatile int*)&S.live <= 0) break;
+            __nanosleep(200);
+            continue;
+        }
+        const bool active = ((act >> lane) & 1u) != 0u;
+#else
     const bool hard = MODE == WF2_MODE_HARD ? true : (MODE == WF2_MODE_SPLIT || offload) ? false : (P.hardPhases != 0);
     constexpr bool split = MODE == WF2_MODE_SPLIT;
     // hard-phase schedule: each cycle is two block-synchronous phases,
@@ -702,6 +812,7 @@ __global__ void __launch_bounds__(THREADS, TB_WF2_CTAS_PER_SM) k_wavefront2(Laun
             idleSpins = 0;
         }
         const bool active = lane < n;
+#endif
 
         if (stage == WF2_Q_R) {
             // ===================== R: splat the finished sample, regenerate =======================
@@ -1007,8 +1118,12 @@ void launch_layout(const LaunchParams& p, int numSMs, cudaStream_t stream, unsig
     const unsigned long long total = p.samplesPerFrame * (unsigned long long)p.numFrames;
     if (total == 0ull) return;
     cudaMemsetAsync(p.sampleCounter, 0, sizeof(unsigned long long), stream);
+#if !defined(TB_WF2_LANEQ)
     const bool split = !p.hardPhases && p.scene.splitValid;
-#ifdef TB_WF2_COLD_SMEM
+#endif
+#if defined(TB_WF2_LANEQ)
+    launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_GENERIC>(p, numSMs, stream, total);
+#elif defined(TB_WF2_COLD_SMEM)
     if (p.hardPhases) launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_HARD>(p, numSMs, stream, total);
     else if (split) launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_SPLIT>(p, numSMs, stream, total);
     else launch_wavefront2_t<TB_WF2_THREADS, WF2_MODE_GENERIC>(p, numSMs, stream, total);

@@ -17,7 +17,7 @@ import tempfile
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "tinsel_b200", "libtinsel_b200.so")
+LIB = os.environ.get("TINSEL_B200_LIB") or os.path.join(ROOT, "tinsel_b200", "libtinsel_b200.so")
 
 
 def line_table(kernel):
@@ -68,16 +68,13 @@ def function_of_line():
 
 
 def mangled_fragment(rep, kernel):
-    """`k_wavefront2<512, 2>` in the report -> `k_wavefront2ILi512ELi2E`, so that the line table of
-    exactly that template instantiation is used (the library holds several)."""
-    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
+    """The mangled name of the profiled kernel (`_ZN6wf2_lq12k_wavefront2ILi512ELi0EEEv12LaunchParamsy`), so that
+    the line table of exactly that instantiation is used: the library holds the same template in several
+    namespaces (the layouts of wavefront2.cuh) and with several arguments."""
+    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-kernel-base", "mangled"], text=True, stderr=subprocess.DEVNULL)
     rows = list(csv.reader(io.StringIO(raw)))
     name = rows[2][rows[0].index("Kernel Name")]
-    m = re.search(r"(\w+)<([^>]*)>", name)
-    if not m or kernel not in m.group(1):
-        return kernel
-    args = "".join("Li%sE" % a.strip() for a in m.group(2).split(","))
-    return "%sI%sE" % (m.group(1), args)
+    return name if kernel in name else kernel
 
 
 def main():
