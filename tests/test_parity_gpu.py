@@ -334,6 +334,20 @@ def test_streamed_readback_delivers_final_rows(case):
     snap.close()
 
 
+def test_lane_queue_layout_on_small_frames(monkeypatch):
+    """Launches of fewer than six samples per slot run the ring queues by default (kernels.cu:
+    launch_wavefront2), so the small-frame feature tests above never see the lane-owned layout: force it
+    (TINSEL_B200_QUEUES=lanes) and repeat the ones that exercise ragged tiles, tile padding, the band counters
+    of the streamed read-back, interleaved shards and batched frames."""
+    monkeypatch.setenv("TINSEL_B200_QUEUES", "lanes")
+    for size in [(1, 1), (37, 23), (129, 65)]:
+        test_ragged_image_sizes(size)
+    test_batched_render_equals_repeated_render()
+    test_interleaved_shards_sum_to_full_image()
+    for case in [("cornell", (1021, 515), 1, 0.0), ("cornell", (512, 512), 3, 0.0), ("cornell", (300, 900), 1, 3.5), ("cornell", (5, 3), 1, 0.0)]:
+        test_streamed_readback_delivers_final_rows(case)
+
+
 # BASELINE.json configs at their full image sizes (C2 cornell 1024^2, C3 ajax 1024^2, C4 veach
 # 1920x1080 with clamp 4, C5 env 2048^2): one frame of every config traced per sample on the GPU
 # and by the reference's PathTrace on all host cores -- bit-exact -- and the same frame through

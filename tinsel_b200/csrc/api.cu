@@ -683,11 +683,13 @@ bool upload_image(tb200_renderer* r, const SceneImage& img)
         const char* cta = getenv("TINSEL_B200_CTA");
         if (cta && atoi(cta) == 768) r->wideCta = 1;
         if (cta && atoi(cta) == 512) r->wideCta = 0;
-        // Lane-owned slots with bit-set queues: scenes held on chip under the free-running scheduler (the launch
-        // falls back to the ring queues for every other combination).  TINSEL_B200_QUEUES=ring|lanes.
+        // Lane-owned slots with bit-set queues: scenes held on chip under the free-running scheduler, for launches
+        // big enough to reach a steady state (kernels.cu: launch_wavefront2; every other combination runs the
+        // ring queues).  TINSEL_B200_QUEUES=ring|lanes forces one or the other whatever the launch size.
         r->laneQueues = 1;
         const char* queues = getenv("TINSEL_B200_QUEUES");
         if (queues && strcmp(queues, "ring") == 0) r->laneQueues = 0;
+        if (queues && strcmp(queues, "lanes") == 0) r->laneQueues = 2;
     }
     // one element of padding each: the kernels' bulk copies round their length up to 16 bytes
     if (!upload(img.prims, &r->dPrims, h2d, 1)) return false;

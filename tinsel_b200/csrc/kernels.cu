@@ -338,9 +338,14 @@ namespace wf2_lq {
 
 void launch_wavefront2(const LaunchParams& p, int numSMs, cudaStream_t stream, unsigned long long* launchCount)
 {
+    // The lane-owned layout wins in the steady state (cornell 32 spp: +15 %) and loses while the slots fill and
+    // drain (one 1-spp frame of 1024 x 512: -3 %, of 1024 x 132, a slab of an 8-GPU render: -24 %): launches of
+    // fewer than six samples per slot keep the rings.
+    const unsigned long long total = p.samplesPerFrame * (unsigned long long)p.numFrames;
+    const bool small = total < 6ull * (unsigned long long)(numSMs > 0 ? numSMs : 148) * 1024ull;
     if (p.wideCta || wavefront2_wants_offload(p))
         wf2_l2::launch_layout(p, numSMs, stream, launchCount);
-    else if (p.laneQueues && !p.hardPhases && !p.scene.splitValid)
+    else if (!p.hardPhases && !p.scene.splitValid && (p.laneQueues == 2 || (p.laneQueues == 1 && !small)))
         wf2_lq::launch_layout(p, numSMs, stream, launchCount);
     else
         wf2_smem::launch_layout(p, numSMs, stream, launchCount);

@@ -32,7 +32,7 @@ struct LaunchParams {
     unsigned long long* sampleCounter;   // per-renderer work counter of the wavefront kernel
     int hardPhases;       // wavefront scheduling mode: 1 = block-synchronous stages, 0 = free-running warps
     int wideCta;          // 1 = 768-thread CTAs (deep mesh BVHs), 0 = 512
-    int laneQueues;       // 1 = lane-owned slots with bit-set stage queues (free-running on-chip scenes), 0 = ring queues
+    int laneQueues;       // lane-owned slots with bit-set stage queues (free-running on-chip scenes): 0 never, 1 for big launches, 2 always
     int frame0;           // first frame (sample index per pixel)
     int numFrames;        // frames to trace in this launch
     int firstRow;         // pixel rows [firstRow, firstRow+numRows) are traced ...
