@@ -231,8 +231,7 @@ TB_DEV unsigned wf2_claim_fullest(Wf2Shared& S, int stick, int& slot, int& stage
     const int rot = (int)(threadIdx.x >> 5) * 2 + 1;
     for (;;) {
         // the preference and the four queue words load side by side (no load depends on another)
-        int pref = 0;
-        if (lane == 0) pref = *(volatile int*)&S.pref;
+        int pref = *(volatile int*)&S.pref;   // every lane loads (a broadcast, no branch); lane 0's copy is the one used
         const unsigned m0 = *(volatile unsigned int*)&S.lq[0][lane], m1 = *(volatile unsigned int*)&S.lq[1][lane];
         const unsigned m2 = *(volatile unsigned int*)&S.lq[2][lane], m3 = *(volatile unsigned int*)&S.lq[3][lane];
         pref = __shfl_sync(0xffffffffu, pref, 0);

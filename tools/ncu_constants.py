@@ -29,7 +29,7 @@ def main():
     path = os.path.join(ROOT, "tools", "algo_bytes.json")
     doc = json.load(open(path))
     ncu = doc["scenes"][scene].setdefault("ncu", {})
-    ncu["kernel"] = vals[hdr.index("Kernel Name")]
+    ncu["kernel"] = subprocess.check_output(["c++filt", vals[hdr.index("Kernel Name")]], text=True).strip()   # with its namespace
     ncu["inst_per_sample"] = num("smsp__inst_executed.sum") / samples
     ncu["lanes"] = num("smsp__thread_inst_executed_per_inst_executed.ratio")
     ncu["dram_bytes_per_sample"] = (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / samples
